@@ -1,0 +1,243 @@
+/*
+ * scb200.h -- C ABI of libscb200.so, the B200 (sm_100a) implementation of the
+ * springcraft elastic-network hot path.
+ *
+ * The reference (biotite-dev/springcraft 0.3.0) has no FFI layer: the seam is
+ * its Python API.  Every entry point below replaces the
+ * Python/NumPy code cited next to it; springcraft_b200/ binds them with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns an int status: 0 = OK, <0 = scb_status error.
+ *     No exception crosses the ABI.
+ *   - unless the name ends in _host, every pointer is a DEVICE pointer owned by
+ *     the caller and `stream` is a cudaStream_t passed as void*.  Functions are
+ *     asynchronous with respect to the host unless documented otherwise.
+ *   - no hidden global state: re-entrant per stream.
+ *   - B = number of structures in the batch (ensemble), n = nodes per structure,
+ *     D = 1 (GNM / Kirchhoff) or 3 (ANM / Hessian), N = D*n,
+ *     P = number of ORDERED contact pairs of the whole batch.
+ *   - coordinates are SoA: xyz[B][3][n] fp64.
+ *   - the neighbour list is one CSR over the B*n rows of the batch:
+ *     rowptr[B*n+1] int64 (global offsets), col[P] int32 (node index inside the
+ *     structure), columns ascending inside a row  ==> walking it reproduces the
+ *     reference's np.where(adj) pair order (interaction.py:177-178).
+ *   - matrices are BSR with DxD blocks: offdiag[P][D*D] (row-major block),
+ *     diag[B*n][D*D].
+ *   - block vectors are row-major X[B][N][b] (b contiguous).
+ */
+#ifndef SCB200_H
+#define SCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_VERSION 100
+
+typedef enum scb_status {
+    SCB_OK = 0,
+    SCB_ERR_INVALID = -1,       /* bad argument                      -> ValueError   */
+    SCB_ERR_CUDA = -2,          /* CUDA runtime error                -> RuntimeError */
+    SCB_ERR_ABOVE_CUTOFF = -3,  /* Tabulated bin above last edge     -> ValueError (forcefield.py:526-533) */
+    SCB_ERR_WORKSPACE = -4,     /* workspace too small               -> RuntimeError */
+    SCB_ERR_NOT_CONVERGED = -5, /* eigensolver hit max iterations    -> RuntimeError */
+    SCB_ERR_UNSUPPORTED = -6    /* size / mode not implemented       -> NotImplementedError */
+} scb_status;
+
+/* force-field kinds: forcefield.py:264-289, 292-330, 333-366, 369-545 */
+enum {
+    SCB_FF_INVARIANT = 0,
+    SCB_FF_HINSEN = 1,
+    SCB_FF_PFREE = 2,
+    SCB_FF_TABULATED = 3,        /* 20x20xk residue-pair tables + per-atom attributes */
+    SCB_FF_TABULATED_DENSE = 4,  /* explicit (n,n,k) float32 interaction_matrix (forcefield.py:429-434) */
+    SCB_FF_EXTERNAL = 5          /* caller-supplied fc[P] (user ForceField subclass, doc/advanced.rst) */
+};
+
+/* POD force-field descriptor.  All pointers are device pointers (or NULL). */
+typedef struct scb_ff_desc {
+    int32_t kind;
+    int32_t nbins;             /* tabulated: number of distance bins k (>=1)            */
+    int32_t patched;           /* PatchedForceField semantics (forcefield.py:183-226)   */
+    int32_t n_pair_on;         /* number of switched-on pairs                           */
+    double cutoff_sq;          /* cutoff**2, or < 0 for "no cutoff" (all pairs)         */
+    const float *bonded;       /* [20][20][k]                                           */
+    const float *intra;        /* [20][20][k]                                           */
+    const float *inter;        /* [20][20][k]                                           */
+    const double *edges_sq;    /* [k] squared bin edges (NULL when k==1)                */
+    const uint8_t *res_type;   /* [n] residue index in ACDEFGHIKLMNPQRSTVWY order       */
+    const int32_t *chain;      /* [n] chain label id                                    */
+    const uint8_t *bonded_next;/* [n] atom a and a+1 are peptide bonded                 */
+    const float *dense_table;  /* [n][n][k] for SCB_FF_TABULATED_DENSE                  */
+    const double *external_fc; /* [P] for SCB_FF_EXTERNAL                               */
+    const int32_t *pair_on;    /* [n_pair_on][2]                                        */
+    const double *pair_on_fc;  /* [n_pair_on]                                           */
+} scb_ff_desc;
+
+/* contact patches applied to the adjacency (interaction.py:193-213) */
+typedef struct scb_patch {
+    int32_t n_pair_off;
+    int32_t n_pair_on;
+    const uint8_t *dead;       /* [n] 1 = contact_shutdown atom, or NULL                */
+    const int32_t *pair_off;   /* [n_pair_off][2] or NULL                               */
+    const int32_t *pair_on;    /* [n_pair_on][2]  or NULL                               */
+} scb_patch;
+
+int scb_version(void);
+const char *scb_status_string(int status);
+/* last CUDA error text seen by this thread (for SCB_ERR_CUDA) */
+const char *scb_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  contact search.   Replaces interaction.py:149-178 (+ biotite CellList,
+ * interaction.py:155-159) and _patch_adjacency_matrix (interaction.py:193-213).
+ * Criterion: fp64 ((dx*dx)+(dy*dy))+(dz*dz) <= cutoff_sq, no FMA contraction.
+ * Two-phase count -> scan -> fill.
+ * ------------------------------------------------------------------------- */
+/* rowcount[B*n] int32.  use_cell_list != 0 selects the cell-list kernels
+ * (B must be 1); both variants produce identical results. */
+int scb_contacts_count(const double *xyz, int B, int n, double cutoff_sq,
+                       const scb_patch *patch, int use_cell_list,
+                       int32_t *rowcount, void *stream);
+/* exclusive scan of rowcount -> rowptr[B*n+1] (int64); scratch >= scb_scan_scratch_bytes */
+size_t scb_scan_scratch_bytes(int64_t nrows);
+int scb_contacts_scan(const int32_t *rowcount, int64_t nrows, int64_t *rowptr,
+                      void *scratch, void *stream);
+int scb_contacts_fill(const double *xyz, int B, int n, double cutoff_sq,
+                      const scb_patch *patch, int use_cell_list,
+                      const int64_t *rowptr, int32_t *col, void *stream);
+/* pairs[P][2] int64 (interaction.py:177-178); struct-local node indices */
+int scb_pairs_materialize(const int64_t *rowptr, const int32_t *col, int B, int n,
+                          int64_t *pairs, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K2  fused force constant + Kirchhoff / Hessian block assembly.
+ * Replaces ForceField.force_constant (forcefield.py:183-226,283-284,318-326,
+ * 361-362,515-533) + compute_kirchhoff / compute_hessian (interaction.py:47-52,
+ * 93-109) + mass weighting (anm.py:89-96,112-113; gnm.py:85-89,105-106).
+ * Off-diagonal block = ((-fc/sq)*d_a)*d_b; diagonal = -(sum over the row's
+ * blocks in ascending column order)  => bit-identical to the reference.
+ * masses: [n] (shared by the batch) or NULL.  gersh[B]: optional upper bound
+ * of the spectrum (Gershgorin), or NULL.  status_flag: device int32, set to
+ * SCB_ERR_ABOVE_CUTOFF when a tabulated lookup falls above the last edge.
+ * ------------------------------------------------------------------------- */
+int scb_assemble(int D, const double *xyz, int B, int n, const scb_ff_desc *ff,
+                 const int64_t *rowptr, const int32_t *col, const double *masses,
+                 double *offdiag, double *diag, double *gersh, int32_t *status_flag,
+                 void *stream);
+/* ForceField.force_constant(atom_i, atom_j, sq_distance) for explicit triples
+ * (forcefield.py:67-95): out[P] fp64 (tabulated values are float32 widened). */
+int scb_force_constant(const scb_ff_desc *ff, int n, const int32_t *atom_i,
+                       const int32_t *atom_j, const double *sq, int64_t P, double *out,
+                       int32_t *status_flag, void *stream);
+/* disp[P][3] = x_j - x_i (may be NULL) and sq[P] for the CSR pairs
+ * (interaction.py:182-184); feeds user-defined ForceField callbacks. */
+int scb_pair_geometry(const double *xyz, int B, int n, const int64_t *rowptr,
+                      const int32_t *col, double *disp, double *sq, void *stream);
+/* dense [B][N][N] row-major (the reference's return layout, interaction.py:106-109) */
+int scb_densify(int D, int B, int n, const int64_t *rowptr, const int32_t *col,
+                const double *offdiag, const double *diag, double *dense, void *stream);
+/* all-pairs force fields (cutoff None): dense row slab rows [row0,row1) of the
+ * (N x N) matrix of ONE structure, written to dense[(row1-row0)*D][N]; diagonal
+ * blocks included (local row sums).  SURVEY 8e config C4. */
+int scb_assemble_dense_allpairs(int D, const double *xyz, int n, const scb_ff_desc *ff,
+                                const double *masses, int row0, int row1,
+                                double *dense, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K3  eigensolvers.  Replace nma.eigen / np.linalg.eigh (nma.py:29-63).
+ * ------------------------------------------------------------------------- */
+/* y = H x on block vectors:  Y[B][N][b] = BSR * X[B][N][b]  (b = 32, 64 or 128) */
+int scb_spmm(int D, int B, int n, const int64_t *rowptr, const int32_t *col,
+             const double *offdiag, const double *diag, const double *X, double *Y,
+             int b, void *stream);
+/* orthonormal basis of the analytic null space (rigid-body modes, mass weighted
+ * when masses != NULL): Z[B][N][nz], nz = 6 (D=3) or 1 (D=1) */
+int scb_rigid_basis(int D, const double *xyz, int B, int n, const double *masses,
+                    double *Z, void *stream);
+/* lowest-k eigensolver: Chebyshev-filtered subspace iteration on the BSR SpMM
+ * with a dense Rayleigh-Ritz (Jacobi) step.  Computes the b lowest modes of the
+ * operator deflated by Z (pass nz=0/Z=NULL for no deflation); the first `k`
+ * are converged to ||H x - theta x|| <= tol * theta_k.
+ *   eigval[B][b], X[B][N][b] (column q = mode q), resid[B][b], iters[B].
+ * Host-synchronous (polls a device convergence counter once per outer iteration).
+ */
+size_t scb_eig_lowest_workspace_bytes(int D, int B, int n, int b, int nz);
+int scb_eig_lowest(int D, int B, int n, const int64_t *rowptr, const int32_t *col,
+                   const double *offdiag, const double *diag, const double *gersh,
+                   const double *Z, int nz, int k, int b, double tol, int max_outer,
+                   int degree, uint64_t seed, double *eigval, double *X, double *resid,
+                   int32_t *iters, void *workspace, size_t workspace_bytes, void *stream);
+/* full symmetric eigendecomposition of dense A[B][N][N] (lower triangle is
+ * referenced, like LAPACK dsyevd behind np.linalg.eigh): eigval[B][N] ascending,
+ * modes[B][N][N] with ROW k = mode k (nma.py:63).  A is destroyed. */
+size_t scb_eig_full_workspace_bytes(int B, int N);
+int scb_eig_full(int B, int N, double *A, double *eigval, double *modes,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  fluctuation / covariance products (nma.py:108-359, 422-473).
+ * modes are ROW-major per mode: modes[B][m][N]; lam[B][m].  `scale` carries
+ * tem*tem_factors (and 8*pi^2/3 for B-factors, nma.py:228).
+ * ------------------------------------------------------------------------- */
+/* msf[B][n] = scale * sum_k (sum_a modes[k][D*i+a]^2) / lam[k]   (nma.py:145-183) */
+int scb_msf(int D, int B, int n, int m, const double *lam, const double *modes,
+            double scale, double *msf, void *stream);
+/* same, reading the eigensolver's column layout X[B][N][b], modes k0..k0+m-1 */
+int scb_msf_cols(int D, int B, int n, int b, int k0, int m, const double *eigval,
+                 const double *X, double scale, double *msf, void *stream);
+/* dcc rows [row0,row1) of sum_k U_k U_k^T / lam_k (FP64 tensor-core DMMA):
+ * out[(row1-row0)][n]; norm != 0 divides by sqrt(d_ii d_jj) (nma.py:338-357) */
+int scb_dcc(int D, int n, int m, const double *lam, const double *modes, int norm,
+            double scale, int row0, int row1, double *out, void *workspace,
+            size_t workspace_bytes, void *stream);
+size_t scb_dcc_workspace_bytes(int D, int n, int m);
+/* covariance rows [row0,row1) = sum_k u_k u_k^T / lam_k   out[(row1-row0)][N]
+ * (the pinv of anm.py:132-136 restricted to the given modes) */
+int scb_covariance(int N, int m, const double *lam, const double *modes, int row0,
+                   int row1, double *out, void *workspace, size_t workspace_bytes,
+                   void *stream);
+/* linear response dr[N] = sum_k u_k (u_k . f) / lam_k   (nma.py:473) */
+int scb_linear_response(int N, int m, const double *lam, const double *modes,
+                        const double *force, double *out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+/* modes[B][m][N] <- X[B][N][b] columns k0..k0+m-1 (transpose to the reference's
+ * "eigenvectors as rows" layout) */
+int scb_export_modes(int B, int N, int b, int k0, int m, const double *X, double *modes,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Whole-path entry point with HOST buffers (H2D and D2H inside): contacts ->
+ * assembly -> lowest-k modes -> MSF for an ensemble of B conformations of one
+ * n-node structure.  This is what a reference-side plugin would call in place
+ * of   for c in conformations: ANM(c, ff).eigen()/mean_square_fluctuation(...)
+ *   coord_host[B][n][3] fp64 (the reference's (n,3) layout per structure)
+ *   ff: descriptor whose pointers are DEVICE pointers (tables are uploaded once
+ *       by the caller and shared by the batch)
+ *   eigval_host[B][k], msf_host[B][n], modes_host[B][k][N] or NULL
+ *   k non-trivial modes (indices ntriv..ntriv+k-1 of the reference's ordering)
+ * Returns 0 or a negative scb_status; n_pairs_out receives P (may be NULL).
+ * ------------------------------------------------------------------------- */
+/* same path with DEVICE buffers (xyz SoA [B][3][n]; outputs on the device) */
+int scb_enm_ensemble(int D, const double *xyz, int B, int n, const scb_ff_desc *ff,
+                     const scb_patch *patch, const double *masses_dev, int k, double tol,
+                     double *eigval /*[B][k]*/, double *msf /*[B][n]*/,
+                     double *modes /*[B][k][N] or NULL*/, int32_t *iters /*[B] or NULL*/,
+                     int64_t *n_pairs_out, void *stream);
+/* AoS (n,3) -> SoA [3][n] per structure (struc.coord layout -> kernel layout) */
+int scb_coords_to_soa(const double *coord_aos, int B, int n, double *xyz_soa, void *stream);
+int scb_enm_ensemble_host(int D, const double *coord_host, int B, int n,
+                          const scb_ff_desc *ff, const scb_patch *patch,
+                          const double *masses_dev, int k, double tol,
+                          double *eigval_host, double *msf_host, double *modes_host,
+                          int64_t *n_pairs_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCB200_H */

@@ -235,7 +235,7 @@ def _fc_base(spec, pairs, sq):
         out = np.where(same, spec.intra[ti, tj, b], spec.inter[ti, tj, b]).astype(np.float32)
         lo = np.minimum(i, j)
         bonded = (np.abs(i - j) == 1) & spec.bonded_next[lo]
-        hi = lo + 1
+        hi = np.minimum(lo + 1, len(spec.res_type) - 1)
         # forcefield.py:504-509: both orientations take bonded[type_lo, type_hi]
         out = np.where(bonded, spec.bonded[spec.res_type[lo], spec.res_type[hi], b], out)
         out = np.where(i == j, np.float32(0), out)   # forcefield.py:512-513

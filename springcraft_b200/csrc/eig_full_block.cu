@@ -1,0 +1,310 @@
+// K3c (large): two-sided BLOCK Jacobi for dense symmetric matrices, full
+// spectrum.  Replaces LAPACK dsyevd behind np.linalg.eigh (nma.py:61) and
+// np.linalg.pinv (anm.py:135) when every mode is requested.
+//
+// The matrix is cut into column blocks of width 32.  A round-robin tournament
+// pairs the blocks; for each pair (I,J) the 64x64 pivot sub-matrix is fully
+// diagonalised in shared memory by cyclic Jacobi (one CTA per pair), giving an
+// orthogonal R.  The update A <- R^T A R, V <- V R is applied as two batched
+// passes of 64x64x64 tile products on the FP64 tensor cores (DMMA m8n8k4):
+// all row pairs first, then all column pairs (pairs are disjoint inside a step).
+// Sweeps repeat until the off-diagonal Frobenius norm is ~1e-14 of the total.
+#include "subspace.cuh"
+#include "jacobi.cuh"
+
+namespace scb {
+
+constexpr int kBW = 32;         // block width
+constexpr int kPW = 2 * kBW;    // pivot order
+constexpr int kTLD = 68;        // padded leading dimension of the smem tiles (conflict-free DMMA fragments)
+
+__device__ __forceinline__ double bj_block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+}
+
+__device__ __forceinline__ void block_pair(int nb, int step, int k, int* I, int* J) {
+    // circle method: player nb-1 is fixed, the others rotate
+    int p, q;
+    if (k == 0) { p = nb - 1; q = step % (nb - 1); }
+    else { p = (step + k) % (nb - 1); q = (step - k + (nb - 1)) % (nb - 1); }
+    *I = min(p, q);
+    *J = max(p, q);
+}
+
+// Ap (Np x Np) <- symmetric extension of the lower triangle of A (N x N), zero padded; V <- I
+__global__ void bj_init_kernel(int N, int Np, const double* __restrict__ A, double* __restrict__ Ap,
+                               double* __restrict__ V) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)Np * Np) return;
+    const int i = (int)(q / Np), j = (int)(q % Np);
+    double v = 0.0;
+    if (i < N && j < N) v = (j <= i) ? A[(int64_t)i * N + j] : A[(int64_t)j * N + i];
+    Ap[q] = v;
+    V[q] = (i == j) ? 1.0 : 0.0;
+}
+
+// one CTA per block pair: diagonalise the 64x64 pivot, write R[pair][64][64]
+__global__ void __launch_bounds__(256)
+bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double* __restrict__ R,
+                int32_t* __restrict__ active) {
+    constexpr int LD = kPW + 1;
+    extern __shared__ double sm[];
+    double* S = sm;
+    double* V = S + kPW * LD;
+    __shared__ double cs[kPW / 2], sn[kPW / 2], red[8];
+    __shared__ int pp[kPW / 2], qq[kPW / 2];
+    int I, J;
+    block_pair(nb, step, blockIdx.x, &I, &J);
+    const int tid = threadIdx.x;
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        const int r = q / kPW, c = q % kPW;
+        const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
+        const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
+        S[r * LD + c] = 0.5 * (Ap[(int64_t)gr * Np + gc] + Ap[(int64_t)gc * Np + gr]);
+        V[r * LD + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // skip pivots whose coupling block is already negligible
+    double off = 0.0, dg = 0.0;
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        const int r = q / kPW, c = q % kPW;
+        const double v = S[r * LD + c];
+        if (r == c) dg += v * v; else off += v * v;
+    }
+    off = bj_block_sum(off, red);
+    dg = bj_block_sum(dg, red);
+    const bool work = off > 1e-32 * dg && off > 0.0;
+    if (work) jacobi_eigen_smem<LD>(S, V, kPW, cs, sn, pp, qq, red, kPW);
+    double* Rp = R + (int64_t)blockIdx.x * kPW * kPW;
+    for (int q = tid; q < kPW * kPW; q += 256) Rp[q] = V[(q / kPW) * LD + q % kPW];
+    if (tid == 0) active[blockIdx.x] = work ? 1 : 0;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// out(64x64) = L(64x64, row-major in sL) * Rm(64x64, row-major in sR); warp w owns output rows 8w..8w+7
+__device__ __forceinline__ void tile_product(const double* sL, const double* sR, double acc[8][2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll 4
+    for (int k4 = 0; k4 < kPW; k4 += 4) {
+        const double a = sL[(warp * 8 + (lane >> 2)) * kTLD + k4 + (lane & 3)];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double b = sR[(k4 + (lane & 3)) * kTLD + j * 8 + (lane >> 2)];
+            dmma884(acc[j][0], acc[j][1], a, b);
+        }
+    }
+}
+
+// rows pass: [A_I,: ; A_J,:] <- R^T [A_I,: ; A_J,:]   grid (Np/64 column tiles, pairs)
+__global__ void __launch_bounds__(256)
+bj_rows_kernel(int Np, int nb, int step, double* __restrict__ Ap, const double* __restrict__ R,
+               const int32_t* __restrict__ active) {
+    extern __shared__ double sm[];
+    double* sL = sm;               // R^T
+    double* sR = sm + kPW * kTLD;  // the 64 x 64 tile of A
+    if (!active[blockIdx.y]) return;
+    int I, J;
+    block_pair(nb, step, blockIdx.y, &I, &J);
+    const double* Rp = R + (int64_t)blockIdx.y * kPW * kPW;
+    const int c0 = blockIdx.x * kPW;
+    const int tid = threadIdx.x;
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        const int r = q / kPW, c = q % kPW;
+        sL[c * kTLD + r] = Rp[q];  // transpose
+        const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
+        sR[r * kTLD + c] = Ap[(int64_t)gr * Np + c0 + c];
+    }
+    __syncthreads();
+    double acc[8][2];
+    tile_product(sL, sR, acc);
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r = warp * 8 + (lane >> 2);
+    const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j * 8 + 2 * (lane & 3);
+        *reinterpret_cast<double2*>(&Ap[(int64_t)gr * Np + c]) = make_double2(acc[j][0], acc[j][1]);
+    }
+}
+
+// columns pass: [M_:,I M_:,J] <- [M_:,I M_:,J] R for M = A (z=0) and M = V (z=1)
+__global__ void __launch_bounds__(256)
+bj_cols_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __restrict__ V,
+               const double* __restrict__ R, const int32_t* __restrict__ active) {
+    extern __shared__ double sm[];
+    double* sL = sm;               // 64 rows x (I,J) columns
+    double* sR = sm + kPW * kTLD;  // R
+    if (!active[blockIdx.y]) return;
+    int I, J;
+    block_pair(nb, step, blockIdx.y, &I, &J);
+    double* M = blockIdx.z ? V : Ap;
+    const double* Rp = R + (int64_t)blockIdx.y * kPW * kPW;
+    const int r0 = blockIdx.x * kPW;
+    const int tid = threadIdx.x;
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        const int r = q / kPW, c = q % kPW;
+        sR[r * kTLD + c] = Rp[q];
+        const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
+        sL[r * kTLD + c] = M[(int64_t)(r0 + r) * Np + gc];
+    }
+    __syncthreads();
+    double acc[8][2];
+    tile_product(sL, sR, acc);
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r = r0 + warp * 8 + (lane >> 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = j * 8 + 2 * (lane & 3);
+        const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
+        *reinterpret_cast<double2*>(&M[(int64_t)r * Np + gc]) = make_double2(acc[j][0], acc[j][1]);
+    }
+}
+
+// norms[0] += sum of squared off-diagonal entries, norms[1] += squared diagonal
+__global__ void __launch_bounds__(256)
+bj_norms_kernel(int Np, const double* __restrict__ Ap, double* __restrict__ norms) {
+    __shared__ double red[8];
+    double off = 0.0, dg = 0.0;
+    const int64_t total = (int64_t)Np * Np;
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
+        const double v = Ap[q];
+        if (q / Np == q % Np) dg += v * v; else off += v * v;
+    }
+    off = bj_block_sum(off, red);
+    dg = bj_block_sum(dg, red);
+    if (threadIdx.x == 0) { atomicAdd(&norms[0], off); atomicAdd(&norms[1], dg); }
+}
+
+// rank of each of the first N diagonal entries (ascending, ties by index)
+__global__ void __launch_bounds__(256)
+bj_rank_kernel(int N, int Np, const double* __restrict__ Ap, int32_t* __restrict__ rank,
+               double* __restrict__ eigval) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double v = Ap[(int64_t)i * Np + i];
+    int r = 0;
+    for (int k = 0; k < N; ++k) {
+        const double u = Ap[(int64_t)k * Np + k];
+        r += (u < v) || (u == v && k < i);
+    }
+    rank[i] = r;
+    eigval[r] = v;
+}
+
+// modes[rank[c]][r] = V[r][c]   (32x32 transpose tiles)
+__global__ void __launch_bounds__(256)
+bj_export_kernel(int N, int Np, const double* __restrict__ V, const int32_t* __restrict__ rank,
+                 double* __restrict__ modes) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int r = r0 + rr, c = c0 + tx;
+        tile[rr][tx] = (r < N && c < N) ? V[(int64_t)r * Np + c] : 0.0;
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 32; cc += 8) {
+        const int c = c0 + cc, r = r0 + tx;
+        if (c < N && r < N) modes[(int64_t)rank[c] * N + r] = tile[tx][cc];
+    }
+}
+
+static int padded_order(int N) {
+    int nb = (int)ceil_div(N, kBW);
+    if (nb % 2) nb += 1;
+    if (nb < 2) nb = 2;
+    return nb * kBW;
+}
+
+struct BjWork {
+    double *Ap, *V, *R, *norms;
+    int32_t *active, *rank;
+};
+
+static void bj_carve(Arena& ar, BjWork* w, int N) {
+    const int Np = padded_order(N);
+    const int nb = Np / kBW;
+    w->Ap = ar.take<double>((size_t)Np * Np);
+    w->V = ar.take<double>((size_t)Np * Np);
+    w->R = ar.take<double>((size_t)(nb / 2) * kPW * kPW);
+    w->norms = ar.take<double>(2);
+    w->active = ar.take<int32_t>(nb / 2);
+    w->rank = ar.take<int32_t>(N);
+}
+
+size_t eig_full_block_workspace_bytes(int B, int N) {
+    (void)B;  // matrices of a batch are processed one after the other
+    Arena ar(nullptr, 0);
+    BjWork w;
+    bj_carve(ar, &w, N);
+    return ar.off + 256;
+}
+
+int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
+    Arena ar(workspace, workspace_bytes);
+    BjWork w;
+    bj_carve(ar, &w, N);
+    if (!ar.ok()) return SCB_ERR_WORKSPACE;
+    const int Np = padded_order(N);
+    const int nb = Np / kBW;
+    const int npairs = nb / 2;
+    const size_t smem_pivot = sizeof(double) * 2 * kPW * (kPW + 1);
+    const size_t smem_tile = sizeof(double) * 2 * kPW * kTLD;
+    static bool configured = false;
+    if (!configured) {
+        SCB_CUDA(cudaFuncSetAttribute(bj_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pivot));
+        SCB_CUDA(cudaFuncSetAttribute(bj_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+        SCB_CUDA(cudaFuncSetAttribute(bj_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+        configured = true;
+    }
+    double* h_norms = nullptr;
+    SCB_CUDA(cudaMallocHost(&h_norms, 2 * sizeof(double)));
+    int status = SCB_OK;
+    for (int s = 0; s < B && status == SCB_OK; ++s) {
+        const double* As = A + (int64_t)s * N * N;
+        bj_init_kernel<<<(unsigned)ceil_div((int64_t)Np * Np, 256), 256, 0, st>>>(N, Np, As, w.Ap, w.V);
+        bool converged = false;
+        for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
+            for (int step = 0; step < nb - 1; ++step) {
+                bj_pivot_kernel<<<npairs, 256, smem_pivot, st>>>(Np, nb, step, w.Ap, w.R, w.active);
+                bj_rows_kernel<<<dim3(Np / kPW, npairs), 256, smem_tile, st>>>(Np, nb, step, w.Ap, w.R, w.active);
+                bj_cols_kernel<<<dim3(Np / kPW, npairs, 2), 256, smem_tile, st>>>(Np, nb, step, w.Ap, w.V, w.R,
+                                                                                 w.active);
+            }
+            cudaMemsetAsync(w.norms, 0, 2 * sizeof(double), st);
+            bj_norms_kernel<<<4 * kNumSM, 256, 0, st>>>(Np, w.Ap, w.norms);
+            if (cudaMemcpyAsync(h_norms, w.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) {
+                set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+                status = SCB_ERR_CUDA;
+                break;
+            }
+            if (h_norms[0] <= 1e-28 * (h_norms[0] + h_norms[1])) converged = true;
+        }
+        if (status != SCB_OK) break;
+        if (!converged) { status = SCB_ERR_NOT_CONVERGED; break; }
+        bj_rank_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, Np, w.Ap, w.rank, eigval + (int64_t)s * N);
+        bj_export_kernel<<<dim3((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 32)), 256, 0, st>>>(
+            N, Np, w.V, w.rank, modes + (int64_t)s * N * N);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); status = SCB_ERR_CUDA; }
+    }
+    cudaFreeHost(h_norms);
+    return status;
+}
+
+}  // namespace scb

@@ -1,0 +1,135 @@
+// K3: lowest-k eigensolver -- Chebyshev-filtered subspace iteration on the BSR
+// SpMM with a dense Rayleigh-Ritz step, batched over the structures of an
+// ensemble.  Replaces np.linalg.eigh (nma.py:61) for the "lowest modes" use.
+//
+// Per outer iteration and structure (all launches cover the whole batch;
+// converged structures are skipped through the device-side `done` flags):
+//   1. filter   X <- p_d(H) X          d fused SpMM+recurrence launches
+//   2. deflate  X <- X - Z Z^T X       analytic null space (rigid-body modes)
+//   3. orth     S = X^T X = L L^T,  X <- X L^-T
+//   4. HX = H X
+//   5. RR       T = X^T HX, S2 = X^T X -> Jacobi -> theta, C ; X <- X C, HX <- HX C
+//   6. residuals ||HX - theta X||, convergence flags, new filter bounds
+// The host polls one int32 (number of active structures) per outer iteration.
+#include "subspace.cuh"
+
+namespace scb {
+
+struct EigWork {
+    double *A, *Bf, *Cf, *HX;    // block vectors [B][N][b]; A is the canonical basis (caller's X)
+    double *S, *T, *Cm, *theta, *rn2, *P, *coef;
+    EigState* state;
+    int32_t *done, *n_active;
+};
+
+static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, int degree_cap, double* X) {
+    const size_t N = (size_t)D * n;
+    const size_t vec = (size_t)B * N * b;
+    w->A = X;
+    w->Bf = ar.take<double>(vec);
+    w->Cf = ar.take<double>(vec);
+    w->HX = ar.take<double>(vec);
+    w->S = ar.take<double>((size_t)B * b * b);
+    w->T = ar.take<double>((size_t)B * b * b);
+    w->Cm = ar.take<double>((size_t)B * b * b);
+    w->theta = ar.take<double>((size_t)B * b);
+    w->rn2 = ar.take<double>((size_t)B * b);
+    w->P = ar.take<double>((size_t)B * 8 * b);
+    w->coef = ar.take<double>((size_t)B * degree_cap * 3);
+    w->state = ar.take<EigState>(B);
+    w->done = ar.take<int32_t>(B);
+    w->n_active = ar.take<int32_t>(1);
+    (void)nz;
+    return ar.off;
+}
+
+constexpr int kDegreeCap = 64;
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" size_t scb_eig_lowest_workspace_bytes(int D, int B, int n, int b, int nz) {
+    Arena ar(nullptr, 0);
+    EigWork w;
+    return carve(ar, &w, D, B, n, b, nz, kDegreeCap, nullptr) + 256;
+}
+
+extern "C" int scb_eig_lowest(int D, int B, int n, const int64_t* rowptr, const int32_t* col,
+                              const double* offdiag, const double* diag, const double* gersh, const double* Z,
+                              int nz, int k, int b, double tol, int max_outer, int degree, uint64_t seed,
+                              double* eigval, double* X, double* resid, int32_t* iters, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!rowptr || !col || !offdiag || !diag || !gersh || !eigval || !X || !resid || !iters || !workspace)
+        return SCB_ERR_INVALID;
+    if ((D != 1 && D != 3) || B < 1 || n < 1 || k < 1 || k > b) return SCB_ERR_INVALID;
+    if (b != 32 && b != 64) return SCB_ERR_UNSUPPORTED;
+    if (degree < 2 || degree > kDegreeCap || max_outer < 1) return SCB_ERR_INVALID;
+    const int64_t N = (int64_t)D * n;
+    if (N < b + nz) return SCB_ERR_UNSUPPORTED;  // tiny systems: use scb_eig_full
+    cudaStream_t st = as_stream(stream);
+    Arena ar(workspace, workspace_bytes);
+    EigWork w;
+    carve(ar, &w, D, B, n, b, nz, kDegreeCap, X);
+    if (!ar.ok()) return SCB_ERR_WORKSPACE;
+    const int32_t* done = w.done;
+
+    SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, st));
+    SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
+    SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
+
+    int32_t* h_active = nullptr;
+    SCB_CUDA(cudaMallocHost(&h_active, sizeof(int32_t)));
+    *h_active = B;
+    int status = SCB_OK;
+    double* cur = w.A;  // block to orthonormalise at the top of the Rayleigh-Ritz stage
+    for (int outer = 0; outer <= max_outer; ++outer) {
+        if (outer > 0) {
+            // ---- 1. Chebyshev filter of degree `degree` applied to the basis in A
+            if ((status = cheb_coef(B, degree, w.state, done, w.coef, st)) != SCB_OK) break;
+            double* prev = w.A;
+            double* curb = w.Bf;
+            double* next = w.Cf;
+            if ((status = spmm_cheb(D, B, n, rowptr, col, offdiag, diag, prev, nullptr, curb, b, w.coef,
+                                    degree * 3, done, st)) != SCB_OK) break;
+            for (int d = 1; d < degree; ++d) {
+                if ((status = spmm_cheb(D, B, n, rowptr, col, offdiag, diag, curb, prev, next, b, w.coef + 3 * d,
+                                        degree * 3, done, st)) != SCB_OK) break;
+                double* t = prev; prev = curb; curb = next; next = t;
+            }
+            if (status != SCB_OK) break;
+            cur = curb;
+        }
+        // ---- 2. deflate the analytic null space
+        if ((status = deflate(B, N, b, nz, Z, cur, w.P, done, st)) != SCB_OK) break;
+        // ---- 3. orthonormalise: A <- cur * L^-T
+        if ((status = gram(B, N, b, cur, cur, w.S, done, st)) != SCB_OK) break;
+        if ((status = small_rr(B, b, w.S, nullptr, w.theta, w.Cm, done, 0, st)) != SCB_OK) break;
+        if ((status = rotate(B, N, b, w.Cm, cur, w.A, nullptr, nullptr, done, st)) != SCB_OK) break;
+        // ---- 4. HX = H A
+        if ((status = spmm_cheb(D, B, n, rowptr, col, offdiag, diag, w.A, nullptr, w.HX, b, nullptr, 0, done,
+                                st)) != SCB_OK) break;
+        // ---- 5. Rayleigh-Ritz on the (nearly orthonormal) basis
+        if ((status = gram(B, N, b, w.A, w.A, w.S, done, st)) != SCB_OK) break;
+        if ((status = gram(B, N, b, w.A, w.HX, w.T, done, st)) != SCB_OK) break;
+        if ((status = small_rr(B, b, w.S, w.T, w.theta, w.Cm, done, 1, st)) != SCB_OK) break;
+        if ((status = rotate(B, N, b, w.Cm, w.A, w.A, w.HX, w.HX, done, st)) != SCB_OK) break;
+        // ---- 6. residuals + state
+        if ((status = zero_active_rn2(B, b, w.rn2, done, st)) != SCB_OK) break;
+        if ((status = residual_norms(B, N, b, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
+        if ((status = state_update(B, b, k, tol, w.theta, w.rn2, w.state, w.done, w.n_active, resid, st)) != SCB_OK)
+            break;
+        if (cudaMemcpyAsync(h_active, w.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+            status = SCB_ERR_CUDA;
+            break;
+        }
+        if (*h_active == 0) break;
+    }
+    const int active = *h_active;
+    cudaFreeHost(h_active);
+    if (status != SCB_OK) return status;
+    SCB_TRY(gather_results(B, b, w.theta, w.state, eigval, iters, st));
+    return active == 0 ? SCB_OK : SCB_ERR_NOT_CONVERGED;
+}

@@ -1,0 +1,36 @@
+// Internal interfaces between the eigensolver translation units.
+#pragma once
+#include "common.cuh"
+
+namespace scb {
+
+struct EigState {
+    double ub;       // upper bound of the spectrum
+    double lo;       // lower edge of the damped interval (largest Ritz value of the block)
+    double a0;       // lowest Ritz value (scaling point of the filter)
+    int32_t iters;
+    int32_t converged;
+};
+
+int spmm_cheb(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
+              const double* diag, const double* X, const double* W, double* Y, int b, const double* coef,
+              int coef_stride, const int32_t* done, cudaStream_t st);
+int gram(int B, int64_t N, int b, const double* A, const double* Bm, double* G, const int32_t* done, cudaStream_t st);
+int small_rr(int B, int b, const double* S, const double* T, double* theta, double* C, const int32_t* done,
+             int mode, cudaStream_t st, int nact = 0);
+int rotate(int B, int64_t N, int b, const double* C, const double* Xin, double* Xout, const double* Yin,
+           double* Yout, const int32_t* done, cudaStream_t st);
+int deflate(int B, int64_t N, int b, int nz, const double* Z, double* X, double* P, const int32_t* done,
+            cudaStream_t st);
+int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, const double* theta, double* rn2,
+                   const int32_t* done, cudaStream_t st);
+int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, cudaStream_t s);
+int zero_active_rn2(int B, int b, double* rn2, const int32_t* done, cudaStream_t s);
+int state_update(int B, int b, int k, double tol, const double* theta, const double* rn2, EigState* st,
+                 int32_t* done, int32_t* n_active, double* resid, cudaStream_t s);
+int cheb_coef(int B, int degree, const EigState* st, const int32_t* done, double* coef, cudaStream_t s);
+int rand_init(int64_t total, uint64_t seed, double* X, cudaStream_t s);
+int gather_results(int B, int b, const double* theta, const EigState* st, double* eigval, int32_t* iters,
+                   cudaStream_t s);
+
+}  // namespace scb

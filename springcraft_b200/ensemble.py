@@ -1,0 +1,65 @@
+"""Ensemble entry point: many conformations of one structure
+through contacts -> assembly -> lowest-k modes -> MSF in batched kernels.
+The reference has no batched API (it rejects ndim != 2, interaction.py:141-142);
+this is the drop-in for the loop ``for c in confs: ANM(c, ff)...``."""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["enm_ensemble", "EnsembleResult"]
+
+
+class EnsembleResult:
+    def __init__(self, eigenvalues, msf, modes, n_pairs, converged):
+        self.eigenvalues = eigenvalues   # (B, k)   non-trivial modes, ascending
+        self.msf = msf                   # (B, n)   MSF from those k modes
+        self.modes = modes               # (B, k, N) or None; rows = modes
+        self.n_pairs = n_pairs           # ordered contact pairs in the batch
+        self.converged = converged
+
+
+def _patch_of(ff, n, keep):
+    from ._engine import _patch_struct
+    return _patch_struct(ff, n, keep)
+
+
+def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=1e-10, return_modes=False,
+                 pinned_out=None):
+    """ANM/GNM of B conformations: coords (B, n, 3) host array (float64).
+
+    Returns the k lowest NON-trivial modes' eigenvalues (reference indices
+    6..6+k-1 for ANM, 1..k for GNM) and ``mean_square_fluctuation(mode_subset=
+    those modes)`` for every conformation.  Host->device and device->host copies
+    happen inside the single C-ABI call ``scb_enm_ensemble_host``."""
+    import torch
+    handle = _lib.require_device()
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    if coords.ndim != 3 or coords.shape[2] != 3:
+        raise ValueError(f"Expected coordinates with shape (B,n,3), got {coords.shape}")
+    B, n = int(coords.shape[0]), int(coords.shape[1])
+    D = 3 if kind == "anm" else 1
+    if force_field.natoms is not None and force_field.natoms != n:
+        raise ValueError(f"Got coordinates for {n} atoms, but forcefield was built for {force_field.natoms} atoms")
+    built = force_field._descriptor(n)
+    if built is None:
+        raise NotImplementedError("user-defined ForceField subclasses are not supported by the batched path")
+    desc, keep = built
+    patch = _patch_of(force_field, n, keep)
+    m_dev = None if masses is None else _lib.to_device(np.asarray(masses, dtype=np.float64), torch.float64)
+    if pinned_out is not None:
+        eig, msf, modes = pinned_out
+    else:
+        eig = np.empty((B, k))
+        msf = np.empty((B, n))
+        modes = np.empty((B, k, D * n)) if return_modes else None
+    npairs = C.c_int64(0)
+    status = handle.scb_enm_ensemble_host(
+        D, coords.ctypes.data_as(C.c_void_p), B, n, C.byref(desc), C.byref(patch) if patch is not None else None,
+        _lib.ptr(m_dev), k, tol, eig.ctypes.data_as(C.c_void_p), msf.ctypes.data_as(C.c_void_p),
+        modes.ctypes.data_as(C.c_void_p) if modes is not None else None, C.byref(npairs), _lib.stream_ptr())
+    _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
+    del keep
+    return EnsembleResult(eig, msf, modes, int(npairs.value), status == 0)

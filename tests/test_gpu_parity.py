@@ -1,0 +1,382 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the springcraft-style
+API) against (i) golden vectors produced by the unmodified reference and
+(ii) the NumPy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): contact sets and Invariant Kirchhoff
+bit-exact; Hessians <= 1e-12 relative; eigenvalues <= 1e-8 relative;
+eigenvector subspaces: sine of the largest principal angle < 1e-6;
+MSF / DCC <= 1e-8.
+"""
+import numpy as np
+import pytest
+
+import springcraft_b200 as sc
+from oracle import enm_oracle as orc
+from .conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+HESS_RTOL = 1e-12
+EIG_RTOL = 1e-8
+ANGLE_TOL = 1e-6
+PROD_RTOL = 1e-8
+
+
+def atoms_of(st, name):
+    return sc.AtomArray(st[f"{name}_coord"], st[f"{name}_res_name"], st[f"{name}_chain_id"], st[f"{name}_res_id"])
+
+
+FF = {
+    "invariant7": lambda a: sc.InvariantForceField(7.0),
+    "invariant13": lambda a: sc.InvariantForceField(13.0),
+    "hinsen": lambda a: sc.HinsenForceField(),
+    "hinsen_cut12": lambda a: sc.HinsenForceField(12.0),
+    "pfree": lambda a: sc.ParameterFreeForceField(),
+    "pfree_cut10": lambda a: sc.ParameterFreeForceField(10.0),
+    "e_anm": lambda a: sc.TabulatedForceField.e_anm(a),
+    "e_anm_mean": lambda a: sc.TabulatedForceField.e_anm(a, nonbonded_mean=True),
+    "e_anm_mj": lambda a: sc.TabulatedForceField.e_anm_mj(a),
+    "e_anm_ke": lambda a: sc.TabulatedForceField.e_anm_ke(a),
+    "sd_enm": lambda a: sc.TabulatedForceField.sd_enm(a),
+    "d_enm": lambda a: sc.TabulatedForceField.d_enm(a),
+    "s_enm_10": lambda a: sc.TabulatedForceField.s_enm_10(a),
+    "s_enm_13": lambda a: sc.TabulatedForceField.s_enm_13(a),
+}
+
+
+def rel_err(a, b):
+    scale = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) / (scale if scale > 0 else 1.0)
+
+
+def subspace_sin(A, B):
+    """sine of the largest principal angle between the row spaces of A and B."""
+    Qa, _ = np.linalg.qr(A.T)
+    Qb, _ = np.linalg.qr(B.T)
+    return np.linalg.norm(Qb - Qa @ (Qa.T @ Qb), 2)
+
+
+# --------------------------------------------------------------------------- K1 + K2
+@pytest.mark.parametrize("cutoff", [5, 10, 15])
+@pytest.mark.parametrize("use_cell_list", [False, True])
+def test_kirchhoff_random500_bit_exact(cutoff, use_cell_list, monkeypatch):
+    """test_interaction.py:11-40 -- ProDy Kirchhoff, both contact kernels."""
+    from springcraft_b200 import _engine
+    monkeypatch.setattr(_engine, "CELL_LIST_MIN_N", 0)  # force the cell-list kernels when asked
+    tp = golden("thirdparty_random500.npz")
+    ref = golden("ref_random500.npz")
+    K, pairs = sc.compute_kirchhoff(tp["coord"], sc.InvariantForceField(cutoff), use_cell_list)
+    assert pairs.dtype == np.int64
+    assert np.array_equal(pairs, ref[f"pairs_{cutoff}_1"])
+    assert np.array_equal(K, tp[f"prody_kirchhoff_{cutoff}"].astype(float))
+
+
+@pytest.mark.parametrize("cutoff", [5, 10, 15])
+def test_hessian_random500(cutoff):
+    ref = golden("ref_random500.npz")
+    tp = golden("thirdparty_random500.npz")
+    H, pairs = sc.compute_hessian(tp["coord"], sc.InvariantForceField(cutoff))
+    b = H.reshape(500, 3, 500, 3).transpose(0, 2, 1, 3)
+    assert np.array_equal(b[pairs[:, 0], pairs[:, 1]], ref[f"hessian_offdiag_{cutoff}"])
+    assert np.array_equal(b[np.arange(500), np.arange(500)], ref[f"hessian_diag_{cutoff}"])
+    assert np.count_nonzero(b) == np.count_nonzero(ref[f"hessian_offdiag_{cutoff}"]) + \
+        np.count_nonzero(ref[f"hessian_diag_{cutoff}"])
+
+
+@pytest.mark.parametrize("key", sorted(FF))
+def test_1l2y_assembly(structures, key):
+    ref = golden("ref_1l2y.npz")
+    atoms = atoms_of(structures, "1l2y")
+    ff = FF[key](atoms)
+    H, pairs = sc.compute_hessian(atoms.coord, ff)
+    K, pairs_k = sc.compute_kirchhoff(atoms.coord, ff)
+    assert np.array_equal(pairs, ref[f"{key}/pairs"])
+    assert np.array_equal(pairs_k, ref[f"{key}/pairs"])
+    if key.startswith("hinsen"):   # pow(): libm vs CUDA, <= 1e-12 relative
+        assert rel_err(K, ref[f"{key}/kirchhoff"]) <= HESS_RTOL
+        assert rel_err(H, ref[f"{key}/hessian"]) <= HESS_RTOL
+    else:
+        assert np.array_equal(K, ref[f"{key}/kirchhoff"])
+        assert np.array_equal(H, ref[f"{key}/hessian"])
+    # mass weighting (anm.py:89-113)
+    anm = sc.ANM(atoms, ff, masses=ref["masses"])
+    assert rel_err(anm.hessian, ref[f"{key}/mw_hessian"]) <= HESS_RTOL
+    gnm = sc.GNM(atoms, ff, masses=ref["masses"])
+    assert rel_err(gnm.kirchhoff, ref[f"{key}/gnm_mw_kirchhoff"]) <= HESS_RTOL
+    if not key.startswith("hinsen"):
+        assert np.array_equal(anm.hessian, ref[f"{key}/mw_hessian"])
+
+
+def test_two_chain_patched():
+    """test_forcefield.py:39-114 fixture: overlapping chains + PatchedForceField."""
+    ref = golden("ref_two_chain.npz")
+    atoms = sc.AtomArray(ref["coord"], ref["res_name"], ref["chain_id"], ref["res_id"])
+    base = sc.InvariantForceField(7.0)
+    K, pairs = sc.compute_kirchhoff(atoms.coord, base)
+    assert np.array_equal(pairs, ref["invariant7/pairs"])
+    assert np.array_equal(K, ref["invariant7/kirchhoff"])
+    patches = {
+        "shutdown": dict(contact_shutdown=ref["shutdown"]),
+        "pair_off": dict(contact_pair_off=ref["pair_off"]),
+        "pair_on": dict(contact_pair_on=ref["pair_on"], force_constants=ref["pair_on_fc"]),
+        "all": dict(contact_shutdown=ref["shutdown"], contact_pair_off=ref["pair_off"],
+                    contact_pair_on=ref["pair_on"], force_constants=ref["pair_on_fc"]),
+    }
+    for tag, kw in patches.items():
+        K, pairs = sc.compute_kirchhoff(atoms.coord, sc.PatchedForceField(base, **kw))
+        assert np.array_equal(pairs, ref[f"patched_{tag}/pairs"]), tag
+        assert np.array_equal(K, ref[f"patched_{tag}/kirchhoff"]), tag
+    for key in ("e_anm", "sd_enm", "d_enm", "s_enm_13"):
+        ff = FF[key](atoms)
+        K, pairs = sc.compute_kirchhoff(atoms.coord, ff)
+        assert np.array_equal(pairs, ref[f"{key}/pairs"])
+        assert np.array_equal(K, ref[f"{key}/kirchhoff"]), key
+        pf = sc.PatchedForceField(ff, contact_pair_off=ref["pair_off"], contact_pair_on=ref["pair_on"],
+                                  force_constants=ref["pair_on_fc"])
+        K, _ = sc.compute_kirchhoff(atoms.coord, pf)
+        assert np.array_equal(K, ref[f"{key}_patched/kirchhoff"]), key
+    shifted = sc.AtomArray(ref["shifted_coord"], ref["res_name"], ref["chain_id"], ref["res_id"])
+    for key in ("e_anm", "sd_enm", "hinsen", "invariant13"):
+        ff = FF[key](shifted)
+        H, pairs = sc.compute_hessian(shifted.coord, ff)
+        assert np.array_equal(pairs, ref[f"shifted_{key}/pairs"])
+        assert rel_err(H, ref[f"shifted_{key}/hessian"]) <= HESS_RTOL, key
+        pf = sc.PatchedForceField(ff, contact_shutdown=ref["shutdown"], contact_pair_off=ref["pair_off"],
+                                  contact_pair_on=ref["pair_on"], force_constants=ref["pair_on_fc"])
+        H, pairs = sc.compute_hessian(shifted.coord, pf)
+        assert np.array_equal(pairs, ref[f"shifted_{key}_patched/pairs"])
+        assert rel_err(H, ref[f"shifted_{key}_patched/hessian"]) <= HESS_RTOL, key
+
+
+@pytest.mark.parametrize("seed", [0, 7])
+@pytest.mark.parametrize("cutoff", [5, 10, 15])
+@pytest.mark.parametrize("use_cell_list", [False, True])
+def test_cloud1000_vs_oracle(seed, cutoff, use_cell_list, monkeypatch):
+    """test_interaction.py:71-89 generator (n=1000, box 50), checked against the oracle."""
+    from springcraft_b200 import _engine
+    monkeypatch.setattr(_engine, "CELL_LIST_MIN_N", 0)
+    np.random.seed(seed)
+    coord = np.random.rand(1000, 3) * 50
+    H, pairs = sc.compute_hessian(coord, sc.InvariantForceField(cutoff), use_cell_list)
+    Ho, pairs_o = orc.compute_hessian(coord, orc.FFSpec("invariant", float(cutoff)))
+    assert np.array_equal(pairs, pairs_o)
+    assert np.array_equal(H, Ho)
+    assert np.allclose(H, H.T)
+
+
+def test_cartesian_index_product_user_forcefield():
+    """test_interaction.py:92-116: user-defined ForceField without cutoff."""
+    class AllConnectedForceField(sc.ForceField):
+        def force_constant(self, atom_i, atom_j, sq_distance):
+            return np.ones(len(atom_i))
+
+    np.random.seed(0)
+    coord = np.random.rand(10, 3) * 50
+    _, pairs = sc.compute_hessian(coord, AllConnectedForceField())
+    m = np.zeros((10, 10), dtype=bool)
+    m[tuple(pairs.T)] = True
+    assert (m == ~np.identity(10).astype(bool)).all()
+
+
+def test_force_constant_method(structures):
+    atoms = atoms_of(structures, "1l2y")
+    rng = np.random.default_rng(0)
+    i = rng.integers(0, 20, 200)
+    j = rng.integers(0, 20, 200)
+    sq = rng.uniform(4.0, 16.4, 200) ** 2
+    pairs = np.stack([i, j], 1)
+    for key, spec in (("hinsen", orc.FFSpec("hinsen")), ("pfree", orc.FFSpec("pfree")),
+                      ("sd_enm", orc.preset_spec("sd_enm", atoms.res_name, atoms.chain_id, atoms.res_id)),
+                      ("e_anm", orc.preset_spec("e_anm", atoms.res_name, atoms.chain_id, atoms.res_id))):
+        got = FF[key](atoms).force_constant(i, j, sq)
+        want = orc.force_constants(spec, pairs, sq)
+        assert got.dtype == want.dtype, key
+        assert np.allclose(got, want, rtol=1e-13, atol=0), key
+    with pytest.raises(ValueError):
+        FF["sd_enm"](atoms).force_constant(np.array([0]), np.array([5]), np.array([17.0 ** 2]))
+
+
+# --------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("key", ["invariant7", "invariant13", "hinsen", "e_anm", "sd_enm", "pfree"])
+def test_1l2y_full_spectrum(structures, key):
+    ref = golden("ref_1l2y.npz")
+    atoms = atoms_of(structures, "1l2y")
+    anm = sc.ANM(atoms, FF[key](atoms))
+    lam, vec = anm.eigen()
+    want = ref[f"{key}/anm_eigval"]
+    scale = np.abs(want).max()
+    assert np.allclose(lam[6:], want[6:], rtol=EIG_RTOL, atol=1e-12 * scale)
+    assert np.abs(lam[:6]).max() <= 1e-9 * scale
+    assert np.allclose(vec @ vec.T, np.eye(60), atol=1e-12)
+    H = ref[f"{key}/hessian"]
+    assert np.abs(H @ vec.T - vec.T * lam).max() <= 1e-11 * scale
+    gnm = sc.GNM(atoms, FF[key](atoms))
+    lam, vec = gnm.eigen()
+    want = ref[f"{key}/gnm_eigval"]
+    assert np.allclose(lam[1:], want[1:], rtol=EIG_RTOL, atol=1e-12 * np.abs(want).max())
+
+
+def test_c2_chain1000_full_spectrum():
+    """Config C2: 1,000-residue chain, Hinsen (all pairs), full spectrum + MSF + B-factor."""
+    ref = golden("ref_c2_chain1000.npz")
+    anm = sc.ANM(ref["coord"], sc.HinsenForceField())
+    assert rel_err(np.diagonal(anm.hessian), ref["hessian_diag"]) <= HESS_RTOL
+    lam, modes = anm.eigen()
+    want = ref["eigval"]
+    assert np.allclose(lam[6:], want[6:], rtol=EIG_RTOL, atol=0)
+    assert np.abs(lam[:6]).max() <= 1e-9 * want.max()
+    assert subspace_sin(modes[6:26], ref["modes_6_26"]) < ANGLE_TOL
+    assert np.allclose(anm.mean_square_fluctuation(), ref["msf"], rtol=PROD_RTOL)
+    assert np.allclose(anm.bfactor(), ref["bfactor"], rtol=PROD_RTOL)
+
+
+@pytest.mark.parametrize("N", [65, 128, 200, 331])
+def test_eig_full_block_random(N):
+    """Block-Jacobi full eigensolver vs LAPACK on random symmetric matrices
+    (including a rank-deficient PSD one), lower triangle referenced."""
+    import torch
+    from springcraft_b200 import _engine
+    rng = np.random.default_rng(N)
+    A = rng.normal(size=(N, N))
+    A = A + A.T
+    if N == 200:
+        G = rng.normal(size=(N, N - 7))
+        A = G @ G.T
+    Al = np.tril(A) + 1e3 * np.triu(rng.normal(size=(N, N)), 1)   # garbage in the strict upper triangle
+    lam, modes = _engine.eig_full_dense(torch.from_numpy(Al).cuda())
+    lam, modes = lam[0].cpu().numpy(), modes[0].cpu().numpy()
+    want = np.linalg.eigvalsh(A)
+    scale = np.abs(want).max()
+    assert np.allclose(lam, want, rtol=0, atol=1e-12 * scale)
+    assert np.allclose(modes @ modes.T, np.eye(N), atol=1e-12)
+    assert np.abs(A @ modes.T - modes.T * lam).max() <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("key", ["e_anm", "sd_enm"])
+@pytest.mark.parametrize("c", [0, 1, 2, 4095])
+def test_c3_lowest_modes(key, c):
+    """Config C3 member: 300-residue chain, lowest 20 non-trivial modes + MSF."""
+    ref = golden("ref_c3_chain300.npz")
+    coord = orc.perturbed_conformation(ref["base"], c)
+    atoms = sc.AtomArray(coord, ref["res_name"], ref["chain_id"], ref["res_id"])
+    ff = FF[key](atoms)
+    anm = sc.ANM(coord, ff)
+    lam, modes = anm.eigen(k=26)
+    want = ref[f"c{c}/{key}/eigval"]
+    assert np.allclose(lam[6:26], want[6:26], rtol=EIG_RTOL, atol=0)
+    assert subspace_sin(modes[6:26], ref[f"c{c}/{key}/modes_6_26"]) < ANGLE_TOL
+    # trivial modes: analytic rigid-body basis, orthonormal and in the null space
+    assert np.allclose(modes[:6] @ modes[:6].T, np.eye(6), atol=1e-12)
+    msf = anm.mean_square_fluctuation(mode_subset=np.arange(6, 26))
+    assert np.allclose(msf, ref[f"c{c}/{key}/msf_6_26"], rtol=PROD_RTOL, atol=0)
+    if c == 0:
+        assert rel_err(anm.hessian, ref[f"c0/{key}/hessian"]) <= HESS_RTOL
+
+
+def test_c3_ensemble_api():
+    ref = golden("ref_c3_chain300.npz")
+    members = [0, 1, 2, 4095]
+    coords = np.stack([orc.perturbed_conformation(ref["base"], c) for c in members])
+    atoms = sc.AtomArray(ref["base"], ref["res_name"], ref["chain_id"], ref["res_id"])
+    for key in ("e_anm", "sd_enm"):
+        res = sc.enm_ensemble(coords, FF[key](atoms), k=20, return_modes=True)
+        assert res.converged
+        for q, c in enumerate(members):
+            assert np.allclose(res.eigenvalues[q], ref[f"c{c}/{key}/eigval"][6:26], rtol=EIG_RTOL, atol=0)
+            assert np.allclose(res.msf[q], ref[f"c{c}/{key}/msf_6_26"], rtol=PROD_RTOL, atol=0)
+            assert subspace_sin(res.modes[q], ref[f"c{c}/{key}/modes_6_26"]) < ANGLE_TOL
+        assert res.n_pairs == sum(int(ref[f"c{c}/{key}/n_pairs"]) for c in members)
+
+
+@pytest.mark.parametrize("key", ["invariant13", "e_anm"])
+def test_7cal_lowest_modes(structures, key):
+    """1,776-residue tetramer (test_anm.py:60-84 structure), lowest modes."""
+    ref = golden("ref_7cal.npz")
+    atoms = atoms_of(structures, "7cal")
+    anm = sc.ANM(atoms, FF[key](atoms))
+    lam, modes = anm.eigen(k=26)
+    want = ref[f"{key}/eigval"]
+    assert np.allclose(lam[6:26], want[6:26], rtol=EIG_RTOL, atol=0)
+    assert subspace_sin(modes[6:26], ref[f"{key}/modes_6_26"]) < ANGLE_TOL
+    msf = anm.mean_square_fluctuation(mode_subset=np.arange(6, 26))
+    assert np.allclose(msf, ref[f"{key}/msf_6_26"], rtol=PROD_RTOL, atol=0)
+
+
+# --------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("key", ["invariant13", "hinsen", "e_anm", "sd_enm", "pfree"])
+def test_1l2y_nma_products(structures, key):
+    ref = golden("ref_1l2y.npz")
+    atoms = atoms_of(structures, "1l2y")
+    anm = sc.ANM(atoms, FF[key](atoms))
+    tol = dict(rtol=1e-8, atol=1e-10 * np.abs(ref[f"{key}/anm_cov"]).max())
+    assert np.allclose(anm.frequencies()[6:], ref[f"{key}/anm_freq"][6:], rtol=EIG_RTOL)
+    assert np.allclose(anm.mean_square_fluctuation(), ref[f"{key}/anm_msf"], rtol=PROD_RTOL)
+    assert np.allclose(anm.mean_square_fluctuation(mode_subset=np.arange(6, 26)), ref[f"{key}/anm_msf_sub"],
+                       rtol=PROD_RTOL)
+    assert np.allclose(anm.mean_square_fluctuation(tem=300, tem_factors=orc.K_B * orc.N_A),
+                       ref[f"{key}/anm_msf_tem"], rtol=PROD_RTOL)
+    assert np.allclose(anm.bfactor(), ref[f"{key}/anm_bfactor"], rtol=PROD_RTOL)
+    assert np.allclose(anm.covariance, ref[f"{key}/anm_cov"], **tol)
+    assert np.allclose(anm.dcc(), ref[f"{key}/anm_dcc"], atol=1e-8)
+    assert np.allclose(anm.dcc(norm=False), ref[f"{key}/anm_dcc_abs"], **tol)
+    assert np.allclose(anm.dcc(mode_subset=np.arange(6, 36)), ref[f"{key}/anm_dcc_sub"], atol=1e-8)
+    assert np.allclose(anm.dcc(mode_subset=np.arange(6, 36), norm=False, tem=300), ref[f"{key}/anm_dcc_sub_tem"],
+                       rtol=1e-8, atol=1e-10 * np.abs(ref[f"{key}/anm_dcc_sub_tem"]).max())
+    assert np.allclose(anm.linear_response(ref["force_unit"]), ref[f"{key}/anm_lr_unit"], **tol)
+    assert np.allclose(anm.linear_response(ref["force_rand"].flatten()), ref[f"{key}/anm_lr_rand"],
+                       rtol=1e-8, atol=1e-9 * np.abs(ref[f"{key}/anm_lr_rand"]).max())
+    prs, eff, sens = anm.prs_effector_sensor()
+    assert np.allclose(prs, ref[f"{key}/anm_prs"], rtol=1e-6)
+    assert np.allclose(eff, ref[f"{key}/anm_eff"], rtol=1e-6)
+    assert np.allclose(sens, ref[f"{key}/anm_sens"], rtol=1e-6)
+    with pytest.raises(ValueError):
+        anm.mean_square_fluctuation(mode_subset=np.array([5, 6, 7]))
+    with pytest.raises(ValueError):
+        anm.linear_response(np.zeros((19, 3)))
+    gnm = sc.GNM(atoms, FF[key](atoms))
+    assert np.allclose(gnm.mean_square_fluctuation(), ref[f"{key}/gnm_msf"], rtol=PROD_RTOL)
+    assert np.allclose(gnm.bfactor(tem=300), ref[f"{key}/gnm_bfactor"], rtol=PROD_RTOL)
+    assert np.allclose(gnm.covariance, ref[f"{key}/gnm_cov"], rtol=1e-8,
+                       atol=1e-10 * np.abs(ref[f"{key}/gnm_cov"]).max())
+    assert np.allclose(gnm.dcc(), ref[f"{key}/gnm_dcc"], atol=1e-8)
+    # nodes that do not move in the selected modes have d_ii ~ 1e-32: their normalised rows are
+    # rounding noise in the reference itself (0/0), so compare the well-defined nodes only
+    dsub = gnm.dcc(mode_subset=np.arange(1, 17), norm=False)
+    live = np.diagonal(dsub) > 1e-10 * np.diagonal(dsub).max()
+    got = gnm.dcc(mode_subset=np.arange(1, 17))
+    assert np.allclose(got[np.ix_(live, live)], ref[f"{key}/gnm_dcc_sub"][np.ix_(live, live)], atol=1e-8)
+    mw = sc.ANM(atoms, FF[key](atoms), masses=ref["masses"])
+    assert np.allclose(mw.eigen()[0][6:], ref[f"{key}/mw_eigval"][6:], rtol=EIG_RTOL)
+    assert np.allclose(mw.dcc(), ref[f"{key}/mw_dcc"], atol=1e-8)
+
+
+def test_setters_and_roundtrip(structures):
+    """anm.py:114-148: covariance <-> hessian through the setters."""
+    ref = golden("ref_1l2y.npz")
+    atoms = atoms_of(structures, "1l2y")
+    anm = sc.ANM(atoms, sc.InvariantForceField(13.0))
+    H = anm.hessian
+    assert anm.hessian is H
+    C = anm.covariance
+    assert np.allclose(H, H @ C @ H, atol=1e-9)
+    assert np.allclose(C, C @ H @ C, atol=1e-12)
+    other = sc.ANM(atoms, sc.InvariantForceField(13.0))
+    other.covariance = C.copy()
+    assert np.allclose(other.hessian, ref["invariant13/hessian"], atol=1e-8)
+    with pytest.raises(IndexError):
+        other.hessian = np.zeros((3, 3))
+    g = sc.GNM(atoms, sc.InvariantForceField(7.0))
+    with pytest.raises(ValueError):
+        g.kirchhoff = np.zeros((3, 3))
+
+
+def test_c5_dcc_linear_response():
+    """Config C5 scaled down: DMMA W W^T contraction from a mode subset."""
+    ref = golden("ref_c5_chain400.npz")
+    coord = ref["coord"]
+    anm = sc.ANM(coord, sc.InvariantForceField(13.0))
+    gnm = sc.GNM(coord, sc.InvariantForceField(10.0))
+    assert np.allclose(anm.dcc(mode_subset=np.arange(6, 56)), ref["anm_dcc_sub"], atol=1e-8)
+    assert np.allclose(anm.dcc(mode_subset=np.arange(6, 56), norm=False), ref["anm_dcc_sub_abs"],
+                       rtol=1e-8, atol=1e-10 * np.abs(ref["anm_dcc_sub_abs"]).max())
+    assert np.allclose(gnm.dcc(mode_subset=np.arange(1, 51)), ref["gnm_dcc_sub"], atol=1e-8)
