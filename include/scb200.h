@@ -92,6 +92,8 @@ int scb_version(void);
 const char *scb_status_string(int status);
 /* last CUDA error text seen by this thread (for SCB_ERR_CUDA) */
 const char *scb_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench accounting) */
+uint64_t scb_launch_count(void);
 
 /* ---------------------------------------------------------------------------
  * K1  contact search.   Replaces interaction.py:149-178 (+ biotite CellList,

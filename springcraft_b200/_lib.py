@@ -66,6 +66,7 @@ SIGNATURES = {
     "scb_version": (_I, []),
     "scb_status_string": (C.c_char_p, [_I]),
     "scb_last_cuda_error": (C.c_char_p, []),
+    "scb_launch_count": (_U64, []),
     "scb_contacts_count": (_I, [_P, _I, _I, _D, C.POINTER(Patch), _I, _P, _P]),
     "scb_scan_scratch_bytes": (_SZ, [_I64]),
     "scb_contacts_scan": (_I, [_P, _I64, _P, _P, _P]),

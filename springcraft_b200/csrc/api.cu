@@ -9,7 +9,11 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line) {
     snprintf(g_last_error, sizeof(g_last_error), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e),
              file, line);
 }
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace scb
+
+extern "C" uint64_t scb_launch_count(void) { return __atomic_load_n(&scb::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int scb_version(void) { return SCB_VERSION; }
 

@@ -12,6 +12,7 @@ constexpr int kWarp = 32;
 constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs (grid sizing only)
 
 void set_last_cuda_error(cudaError_t e, const char* file, int line);
+void count_launches(int n);  // process-wide kernel launch counter (scb_launch_count)
 
 #define SCB_CUDA(expr)                                              \
     do {                                                            \
@@ -22,7 +23,12 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line);
         }                                                           \
     } while (0)
 
-#define SCB_LAUNCH_CHECK() SCB_CUDA(cudaGetLastError())
+// one kernel launch precedes every SCB_LAUNCH_CHECK(); extra launches are counted explicitly
+#define SCB_LAUNCH_CHECK()             \
+    do {                               \
+        ::scb::count_launches(1);      \
+        SCB_CUDA(cudaGetLastError());  \
+    } while (0)
 
 #define SCB_TRY(expr)                 \
     do {                              \

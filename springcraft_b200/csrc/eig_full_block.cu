@@ -277,6 +277,7 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
     for (int s = 0; s < B && status == SCB_OK; ++s) {
         const double* As = A + (int64_t)s * N * N;
         bj_init_kernel<<<(unsigned)ceil_div((int64_t)Np * Np, 256), 256, 0, st>>>(N, Np, As, w.Ap, w.V);
+        count_launches(3);  // init + rank + export
         bool converged = false;
         for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
             for (int step = 0; step < nb - 1; ++step) {
@@ -284,9 +285,11 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
                 bj_rows_kernel<<<dim3(Np / kPW, npairs), 256, smem_tile, st>>>(Np, nb, step, w.Ap, w.R, w.active);
                 bj_cols_kernel<<<dim3(Np / kPW, npairs, 2), 256, smem_tile, st>>>(Np, nb, step, w.Ap, w.V, w.R,
                                                                                  w.active);
+                count_launches(3);
             }
             cudaMemsetAsync(w.norms, 0, 2 * sizeof(double), st);
             bj_norms_kernel<<<4 * kNumSM, 256, 0, st>>>(Np, w.Ap, w.norms);
+            count_launches(1);
             if (cudaMemcpyAsync(h_norms, w.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaStreamSynchronize(st) != cudaSuccess) {
                 set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);

@@ -362,9 +362,11 @@ int deflate(int B, int64_t N, int b, int nz, const double* Z, double* X, double*
     if (b == 32) {
         ztx_kernel<1><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
         subz_kernel<1><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
+        count_launches(1);
     } else if (b == 64) {
         ztx_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
         subz_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
+        count_launches(1);
     } else {
         return SCB_ERR_UNSUPPORTED;
     }

@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["enm_ensemble", "EnsembleResult"]
+__all__ = ["enm_ensemble", "enm_ensemble_device", "EnsembleResult"]
 
 
 class EnsembleResult:
@@ -63,3 +63,28 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=1e-10, 
     _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
     del keep
     return EnsembleResult(eig, msf, modes, int(npairs.value), status == 0)
+
+
+def enm_ensemble_device(xyz_soa, force_field, k=20, kind="anm", masses=None, tol=1e-10, out=None):
+    """Same path with DEVICE buffers: xyz_soa is a (B, 3, n) float64 cuda tensor.
+    Returns (eigval (B,k), msf (B,n), iters (B,), n_pairs, converged); all tensors stay in HBM."""
+    import torch
+    handle = _lib.require_device()
+    B, _, n = (int(x) for x in xyz_soa.shape)
+    D = 3 if kind == "anm" else 1
+    desc, keep = force_field._descriptor(n)
+    patch = _patch_of(force_field, n, keep)
+    m_dev = None if masses is None else _lib.to_device(np.asarray(masses, dtype=np.float64), torch.float64)
+    if out is None:
+        out = (torch.empty((B, k), dtype=torch.float64, device="cuda"),
+               torch.empty((B, n), dtype=torch.float64, device="cuda"),
+               torch.empty(B, dtype=torch.int32, device="cuda"))
+    eig, msf, iters = out
+    npairs = C.c_int64(0)
+    status = handle.scb_enm_ensemble(D, _lib.ptr(xyz_soa), B, n, C.byref(desc),
+                                     C.byref(patch) if patch is not None else None, _lib.ptr(m_dev), k, tol,
+                                     _lib.ptr(eig), _lib.ptr(msf), None, _lib.ptr(iters), C.byref(npairs),
+                                     _lib.stream_ptr())
+    _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
+    del keep
+    return eig, msf, iters, int(npairs.value), status == 0
