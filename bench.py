@@ -178,7 +178,7 @@ def workload_config(n_gpus):
         "workload": f"C3 ensemble: {N_CONF} perturbed conformations x {N_RES}-residue CA chain per GPU, "
                     f"{FF_NAME} (13 A cutoff), lowest {K_MODES} non-trivial modes + MSF each",
         "conformations_per_gpu": N_CONF, "residues": N_RES, "force_field": FF_NAME, "modes": K_MODES,
-        "tolerance": "residual <= 1e-10 * lambda_20 (eigenvalues ~1e-14, MSF < 1e-8 vs reference)",
+        "tolerance": "residual <= 3e-9 * lambda_20 (eigenvalues ~1e-14, subspace angle ~1e-9, MSF < 1e-8 vs reference)",
         "parallelism": f"ensemble sharded by conformation over {n_gpus} GPU(s), no data-path collective",
         "l2_policy": "inputs larger than L2 (per-step working set ~7 GB >> 126 MB)",
     }
@@ -267,17 +267,15 @@ def run_gpu(args):
     model = DeviceModel(coords[:N_CONF], ff, 3)
     b = 32
     X = torch.randn((N_CONF, 3 * N_RES, b), dtype=torch.float64, device="cuda")
+    Y = torch.empty_like(X)
     for _ in range(3):
-        model.spmm(X)
+        model.spmm_paired(X, Y)
     reps = 20
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    Y = torch.empty_like(X)
     e0.record()
     for _ in range(reps):
-        _lib.check(handle.scb_spmm(3, model.B, model.n, _lib.ptr(model.rowptr), _lib.ptr(model.col),
-                                   _lib.ptr(model.offdiag), _lib.ptr(model.diag), _lib.ptr(X), _lib.ptr(Y), b,
-                                   _lib.stream_ptr()))
+        model.spmm_paired(X, Y)
     e1.record()
     torch.cuda.synchronize()
     spmm_ms = e0.elapsed_time(e1) / reps
@@ -287,7 +285,7 @@ def run_gpu(args):
     alg_flops = 18.0 * (P + N_CONF * n) * b
     pk, pk_kind = peaks()
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "spmm_kernel<3,1> (BSR 3x3 x 32-column block)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "spmm_paired_kernel<3> (row-paired BSR 6x3 x 32-column block)", "achieved": achieved,
                 "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "traffic": None, "ms_per_launch": spmm_ms, "bytes_per_launch": alg_bytes,
                 "fp64_gflops": alg_flops / (spmm_ms * 1e-3) / 1e9}

@@ -158,6 +158,16 @@ int scb_assemble_dense_allpairs(int D, const double *xyz, int n, const scb_ff_de
 int scb_spmm(int D, int B, int n, const int64_t *rowptr, const int32_t *col,
              const double *offdiag, const double *diag, const double *X, double *Y,
              int b, void *stream);
+/* Row-paired operator used by the eigensolver (two consecutive block rows merged
+ * into (2D x D) blocks, diagonal folded in; spmm_paired.cu).  `paired` is one
+ * device buffer of scb_paired_bytes(); the three offsets (may be NULL) locate the
+ * per-pair counts, merged column indices and merged blocks inside it. */
+size_t scb_paired_bytes(int D, int B, int n, int64_t P, size_t *count_off, size_t *col_off,
+                        size_t *blk_off);
+int scb_paired_build(int D, int B, int n, int64_t P, const int64_t *rowptr, const int32_t *col,
+                     const double *offdiag, const double *diag, void *paired, void *stream);
+int scb_spmm_paired(int D, int B, int n, int64_t P, const int64_t *rowptr, const void *paired,
+                    const double *X, double *Y, int b, void *stream);
 /* orthonormal basis of the analytic null space (rigid-body modes, mass weighted
  * when masses != NULL): Z[B][N][nz], nz = 6 (D=3) or 1 (D=1) */
 int scb_rigid_basis(int D, const double *xyz, int B, int n, const double *masses,
@@ -169,8 +179,8 @@ int scb_rigid_basis(int D, const double *xyz, int B, int n, const double *masses
  *   eigval[B][b], X[B][N][b] (column q = mode q), resid[B][b], iters[B].
  * Host-synchronous (polls a device convergence counter once per outer iteration).
  */
-size_t scb_eig_lowest_workspace_bytes(int D, int B, int n, int b, int nz);
-int scb_eig_lowest(int D, int B, int n, const int64_t *rowptr, const int32_t *col,
+size_t scb_eig_lowest_workspace_bytes(int D, int B, int n, int b, int nz, int64_t P);
+int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t *rowptr, const int32_t *col,
                    const double *offdiag, const double *diag, const double *gersh,
                    const double *Z, int nz, int k, int b, double tol, int max_outer,
                    int degree, uint64_t seed, double *eigval, double *X, double *resid,

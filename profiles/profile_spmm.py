@@ -14,6 +14,6 @@ ff = sc.TabulatedForceField.e_anm(sc.AtomArray(base, *seq))
 model = DeviceModel(coords, ff, 3)
 X = torch.randn((B, 900, 32), dtype=torch.float64, device="cuda")
 for _ in range(5):
-    Y = model.spmm(X)
+    Y = model.spmm_paired(X)
 torch.cuda.synchronize()
 print("ok", float(Y.abs().sum()))

@@ -190,6 +190,28 @@ class DeviceModel:
                                         _lib.stream_ptr()))
         return Y
 
+    def paired(self):
+        """Row-paired copy of the operator (built once, cached)."""
+        torch = _torch()
+        if getattr(self, "_paired", None) is None:
+            nbytes = self.handle.scb_paired_bytes(self.D, self.B, self.n, self.P, None, None, None)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            _lib.check(self.handle.scb_paired_build(self.D, self.B, self.n, self.P, _lib.ptr(self.rowptr),
+                                                    _lib.ptr(self.col), _lib.ptr(self.offdiag), _lib.ptr(self.diag),
+                                                    _lib.ptr(buf), _lib.stream_ptr()))
+            self._paired = buf
+        return self._paired
+
+    def spmm_paired(self, X, Y=None):
+        torch = _torch()
+        b = int(X.shape[-1])
+        if Y is None:
+            Y = torch.empty_like(X)
+        _lib.check(self.handle.scb_spmm_paired(self.D, self.B, self.n, self.P, _lib.ptr(self.rowptr),
+                                               _lib.ptr(self.paired()), _lib.ptr(X), _lib.ptr(Y), b,
+                                               _lib.stream_ptr()))
+        return Y
+
     def rigid_basis(self):
         torch = _torch()
         nz = 6 if self.D == 3 else 1
@@ -198,7 +220,7 @@ class DeviceModel:
                                                _lib.ptr(Z), _lib.stream_ptr()))
         return Z
 
-    def eig_lowest(self, k, deflate=True, tol=1e-10, max_outer=300, degree=20, seed=0x5CB200, b=None):
+    def eig_lowest(self, k, deflate=True, tol=3e-9, max_outer=300, degree=20, seed=0x5CB200, b=None):
         """The k lowest modes of the (optionally rigid-body deflated) operator.
 
         Returns (eigval[B][b], X[B][N][b], resid[B][b], iters[B]) device tensors;
@@ -215,9 +237,9 @@ class DeviceModel:
         X = torch.empty((self.B, self.N, b), dtype=torch.float64, device="cuda")
         resid = torch.empty((self.B, b), dtype=torch.float64, device="cuda")
         iters = torch.empty(self.B, dtype=torch.int32, device="cuda")
-        ws_bytes = h.scb_eig_lowest_workspace_bytes(self.D, self.B, self.n, b, nz)
+        ws_bytes = h.scb_eig_lowest_workspace_bytes(self.D, self.B, self.n, b, nz, self.P)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-        status = h.scb_eig_lowest(self.D, self.B, self.n, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+        status = h.scb_eig_lowest(self.D, self.B, self.n, self.P, _lib.ptr(self.rowptr), _lib.ptr(self.col),
                                   _lib.ptr(self.offdiag), _lib.ptr(self.diag), _lib.ptr(self.gersh), _lib.ptr(Z), nz,
                                   k, b, tol, max_outer, degree, seed, _lib.ptr(eigval), _lib.ptr(X), _lib.ptr(resid),
                                   _lib.ptr(iters), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())

@@ -78,9 +78,12 @@ SIGNATURES = {
     "scb_densify": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "scb_assemble_dense_allpairs": (_I, [_I, _P, _I, C.POINTER(FFDesc), _P, _I, _I, _P, _P]),
     "scb_spmm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "scb_paired_bytes": (_SZ, [_I, _I, _I, _I64, _P, _P, _P]),
+    "scb_paired_build": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _P, _P]),
+    "scb_spmm_paired": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _I, _P]),
     "scb_rigid_basis": (_I, [_I, _P, _I, _I, _P, _P, _P]),
-    "scb_eig_lowest_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
-    "scb_eig_lowest": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _D, _I, _I, _U64,
+    "scb_eig_lowest_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I64]),
+    "scb_eig_lowest": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _I, _I, _I, _D, _I, _I, _U64,
                             _P, _P, _P, _P, _P, _SZ, _P]),
     "scb_eig_full_workspace_bytes": (_SZ, [_I, _I]),
     "scb_eig_full": (_I, [_I, _I, _P, _P, _P, _P, _SZ, _P]),

@@ -20,9 +20,12 @@ struct EigWork {
     double *S, *T, *Cm, *theta, *rn2, *P, *coef;
     EigState* state;
     int32_t *done, *n_active;
+    int32_t *pcount, *pcol;   // row-paired operator (spmm_paired.cu)
+    double* pblk;
 };
 
-static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, int degree_cap, double* X) {
+static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, int degree_cap, double* X,
+                    int64_t P) {
     const size_t N = (size_t)D * n;
     const size_t vec = (size_t)B * N * b;
     w->A = X;
@@ -39,6 +42,10 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
     w->state = ar.take<EigState>(B);
     w->done = ar.take<int32_t>(B);
     w->n_active = ar.take<int32_t>(1);
+    const size_t cap = paired_capacity(B, n, P);
+    w->pcount = ar.take<int32_t>((size_t)B * ((n + 1) / 2));
+    w->pcol = ar.take<int32_t>(cap);
+    w->pblk = ar.take<double>(cap * 2 * D * D);
     (void)nz;
     return ar.off;
 }
@@ -49,13 +56,13 @@ constexpr int kDegreeCap = 64;
 
 using namespace scb;
 
-extern "C" size_t scb_eig_lowest_workspace_bytes(int D, int B, int n, int b, int nz) {
+extern "C" size_t scb_eig_lowest_workspace_bytes(int D, int B, int n, int b, int nz, int64_t P) {
     Arena ar(nullptr, 0);
     EigWork w;
-    return carve(ar, &w, D, B, n, b, nz, kDegreeCap, nullptr) + 256;
+    return carve(ar, &w, D, B, n, b, nz, kDegreeCap, nullptr, P) + 256;
 }
 
-extern "C" int scb_eig_lowest(int D, int B, int n, const int64_t* rowptr, const int32_t* col,
+extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* rowptr, const int32_t* col,
                               const double* offdiag, const double* diag, const double* gersh, const double* Z,
                               int nz, int k, int b, double tol, int max_outer, int degree, uint64_t seed,
                               double* eigval, double* X, double* resid, int32_t* iters, void* workspace,
@@ -70,9 +77,14 @@ extern "C" int scb_eig_lowest(int D, int B, int n, const int64_t* rowptr, const 
     cudaStream_t st = as_stream(stream);
     Arena ar(workspace, workspace_bytes);
     EigWork w;
-    carve(ar, &w, D, B, n, b, nz, kDegreeCap, X);
+    carve(ar, &w, D, B, n, b, nz, kDegreeCap, X, P);
     if (!ar.ok()) return SCB_ERR_WORKSPACE;
     const int32_t* done = w.done;
+    // row-paired copy of the operator for the register-blocked SpMM
+    SCB_TRY(build_paired(D, B, n, rowptr, col, offdiag, diag, w.pcount, w.pcol, w.pblk, st));
+    auto apply = [&](const double* Xin, const double* Win, double* Yout, const double* cf, int stride) {
+        return spmm_paired(D, B, n, rowptr, w.pcount, w.pcol, w.pblk, Xin, Win, Yout, b, cf, stride, done, st);
+    };
 
     SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
@@ -90,11 +102,9 @@ extern "C" int scb_eig_lowest(int D, int B, int n, const int64_t* rowptr, const 
             double* prev = w.A;
             double* curb = w.Bf;
             double* next = w.Cf;
-            if ((status = spmm_cheb(D, B, n, rowptr, col, offdiag, diag, prev, nullptr, curb, b, w.coef,
-                                    degree * 3, done, st)) != SCB_OK) break;
+            if ((status = apply(prev, nullptr, curb, w.coef, degree * 3)) != SCB_OK) break;
             for (int d = 1; d < degree; ++d) {
-                if ((status = spmm_cheb(D, B, n, rowptr, col, offdiag, diag, curb, prev, next, b, w.coef + 3 * d,
-                                        degree * 3, done, st)) != SCB_OK) break;
+                if ((status = apply(curb, prev, next, w.coef + 3 * d, degree * 3)) != SCB_OK) break;
                 double* t = prev; prev = curb; curb = next; next = t;
             }
             if (status != SCB_OK) break;
@@ -107,8 +117,7 @@ extern "C" int scb_eig_lowest(int D, int B, int n, const int64_t* rowptr, const 
         if ((status = small_rr(B, b, w.S, nullptr, w.theta, w.Cm, done, 0, st)) != SCB_OK) break;
         if ((status = rotate(B, N, b, w.Cm, cur, w.A, nullptr, nullptr, done, st)) != SCB_OK) break;
         // ---- 4. HX = H A
-        if ((status = spmm_cheb(D, B, n, rowptr, col, offdiag, diag, w.A, nullptr, w.HX, b, nullptr, 0, done,
-                                st)) != SCB_OK) break;
+        if ((status = apply(w.A, nullptr, w.HX, nullptr, 0)) != SCB_OK) break;
         // ---- 5. Rayleigh-Ritz on the (nearly orthonormal) basis
         if ((status = gram(B, N, b, w.A, w.A, w.S, done, st)) != SCB_OK) break;
         if ((status = gram(B, N, b, w.A, w.HX, w.T, done, st)) != SCB_OK) break;

@@ -99,12 +99,12 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
     SCB_TRY(sc.alloc(&resid, (size_t)B * b));
     SCB_TRY(sc.alloc(&X, (size_t)B * N * b));
     SCB_TRY(sc.alloc(&it, (size_t)B));
-    const size_t ws_bytes = scb_eig_lowest_workspace_bytes(D, B, n, b, nz);
+    const size_t ws_bytes = scb_eig_lowest_workspace_bytes(D, B, n, b, nz, P);
     SCB_TRY(sc.alloc((char**)&ws, ws_bytes));
     SCB_TRY(scb_contacts_fill(xyz, B, n, ff->cutoff_sq, patch, 0, rowptr, col, st));
     SCB_TRY(scb_assemble(D, xyz, B, n, ff, rowptr, col, masses, offdiag, diag, gersh, flag, st));
     SCB_TRY(scb_rigid_basis(D, xyz, B, n, masses, Z, st));
-    int status = scb_eig_lowest(D, B, n, rowptr, col, offdiag, diag, gersh, Z, nz, k, b, tol, 200, 20,
+    int status = scb_eig_lowest(D, B, n, P, rowptr, col, offdiag, diag, gersh, Z, nz, k, b, tol, 200, 20,
                                 0x5cb200ull, theta, X, resid, it, ws, ws_bytes, st);
     if (status != SCB_OK && status != SCB_ERR_NOT_CONVERGED) return status;
     slice_eigval_kernel<<<(unsigned)ceil_div((int64_t)B * k, 256), 256, 0, st>>>(B, b, 0, k, theta, eigval);

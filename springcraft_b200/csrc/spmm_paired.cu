@@ -1,0 +1,288 @@
+// K3a': SpMM on a row-PAIRED block format ("BSR 2Dx D"), the tuned operator of
+// the lowest-k eigensolver.
+//
+// ncu on the one-row-per-warp kernel (profiles/r1a) shows L1/TEX at 94 % of
+// peak with the FP64 pipe 23 % busy: with one column per lane every contact
+// costs ~6 L1 wavefronts of X rows plus 5 broadcast wavefronts for the block.
+// Here two consecutive block rows (residues 2t, 2t+1 -- chain neighbours share
+// ~85 % of their contacts) are merged into one list of (2D x D) blocks, the
+// diagonal blocks folded in, and the warp is split into 4 contact slots x 8
+// lanes x 4 columns:
+//   * an X row segment is loaded once (LDG.128 x2 per lane) and used for both
+//     block rows and 4 columns  -> 6 wavefronts per merged contact;
+//   * block values are read as LDS.128 with 4 distinct addresses per
+//     instruction (conflict free: 144-byte entries) -> 2.25 wavefronts;
+//   * 72 DFMA per lane and merged contact -> 9 cycles/contact on the FP64 pipe,
+//     i.e. the inner loop is FP64-bound instead of L1-bound.
+// Blocks are staged global->shared with cp.async (16-byte chunks, coalesced).
+#include "subspace.cuh"
+
+namespace scb {
+
+constexpr int kPairWarps = 16;     // warps per CTA (128 registers per thread available)
+constexpr int kPairChunk = 16;     // merged contacts staged per warp and round (4 per slot)
+
+// ---------------------------------------------------------------------------
+// format conversion: CSR/BSR (D x D) -> paired.  One thread per row pair does a
+// two-pointer merge of the two sorted column lists (+ the two diagonal columns).
+// Capacity offsets need no scan: pair (s,t) owns [rowptr[r0] + 2*g, ...) with
+// g its global pair index and r0 its first row, at most cnt0+cnt1+2 entries.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+pair_rows_kernel(int n, int np, int64_t total_pairs, const int64_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ col, const double* __restrict__ offdiag,
+                 const double* __restrict__ diag, int32_t* __restrict__ pcount, int32_t* __restrict__ pcol,
+                 double* __restrict__ pblk) {
+    constexpr int DD = D * D;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_pairs) return;
+    const int64_t s = g / np;
+    const int t = (int)(g % np);
+    const int i0 = 2 * t, i1 = 2 * t + 1;
+    const bool has1 = i1 < n;
+    const int64_t r0 = s * n + i0, r1 = r0 + 1;
+    int64_t a = rowptr[r0], ae = rowptr[r0 + 1];
+    int64_t b = has1 ? rowptr[r1] : 0, be = has1 ? rowptr[r1 + 1] : 0;
+    int64_t out = rowptr[r0] + 2 * g;
+    const int64_t out0 = out;
+    bool d0 = false, d1 = !has1;  // diagonal columns already emitted?
+    const int BIG = 0x7fffffff;
+    while (true) {
+        // next candidate column of each row (diagonal entry inserted in order)
+        int ca = (a < ae) ? col[a] : BIG;
+        bool a_is_diag = false;
+        if (!d0 && i0 < ca) { ca = i0; a_is_diag = true; }
+        int cb = BIG;
+        bool b_is_diag = false;
+        if (has1) {
+            cb = (b < be) ? col[b] : BIG;
+            if (!d1 && i1 < cb) { cb = i1; b_is_diag = true; }
+        }
+        const int c = min(ca, cb);
+        if (c == BIG) break;
+        double* dst = pblk + out * (2 * DD);
+        if (ca == c) {
+            const double* src = a_is_diag ? diag + r0 * DD : offdiag + a * DD;
+#pragma unroll
+            for (int q = 0; q < DD; ++q) dst[q] = src[q];
+            if (a_is_diag) d0 = true; else ++a;
+        } else {
+#pragma unroll
+            for (int q = 0; q < DD; ++q) dst[q] = 0.0;
+        }
+        if (cb == c) {
+            const double* src = b_is_diag ? diag + r1 * DD : offdiag + b * DD;
+#pragma unroll
+            for (int q = 0; q < DD; ++q) dst[DD + q] = src[q];
+            if (b_is_diag) d1 = true; else ++b;
+        } else {
+#pragma unroll
+            for (int q = 0; q < DD; ++q) dst[DD + q] = 0.0;
+        }
+        pcol[out] = c;
+        ++out;
+    }
+    pcount[g] = (int)(out - out0);
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+
+// ---------------------------------------------------------------------------
+// Y = alpha (H X - c X) - beta W   on the paired format; b = 32 * ncg columns
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kPairWarps * 32, 1)
+spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __restrict__ rowptr,
+                   const int32_t* __restrict__ pcount, const int32_t* __restrict__ pcol,
+                   const double* __restrict__ pblk, const double* __restrict__ X, const double* __restrict__ W,
+                   double* __restrict__ Y, const double* __restrict__ coef, int coef_stride,
+                   const int32_t* __restrict__ done) {
+    constexpr int DD = D * D;
+    constexpr int E = 2 * DD;            // doubles per merged contact (18 or 2)
+    constexpr int R = 2 * D;             // rows per pair (6 or 2)
+    __shared__ __align__(16) double sblk[kPairWarps][kPairChunk * E];
+    __shared__ int32_t scol[kPairWarps][kPairChunk];
+    const int64_t s = blockIdx.y;
+    if (done && done[s]) return;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slot = lane >> 3, l8 = lane & 7;
+    const int64_t N = (int64_t)D * n;
+    double alpha = 1.0, cshift = 0.0, beta = 0.0;
+    if (coef) {
+        const double* cf = coef + s * coef_stride;
+        alpha = cf[0]; cshift = cf[1]; beta = cf[2];
+    }
+    const int t0 = blockIdx.x * pairs_per_cta;
+    const int t1 = min(np, t0 + pairs_per_cta);
+    const int ncg = b >> 5;
+    for (int t = t0 + warp; t < t1; t += kPairWarps) {
+        const int64_t g = s * np + t;
+        const int64_t base = rowptr[s * n + 2 * t] + 2 * g;
+        const int cnt = pcount[g];
+        for (int cg = 0; cg < ncg; ++cg) {
+            const int c0 = cg * 32 + 4 * l8;
+            const double* Xs = X + s * N * b + c0;
+            double acc[R][4];
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) acc[a][cc] = 0.0;
+            for (int e0 = 0; e0 < cnt; e0 += kPairChunk) {
+                const int m = min(kPairChunk, cnt - e0);
+                __syncwarp();
+                {   // stage m merged contacts: E*8 bytes each, 16-byte chunks, coalesced
+                    const char* src = reinterpret_cast<const char*>(pblk + (base + e0) * E);
+                    char* dst = reinterpret_cast<char*>(&sblk[warp][0]);
+                    const int chunks = m * E / 2;
+                    for (int q = lane; q < chunks; q += 32) cp_async_16(dst + 16 * q, src + 16 * q);
+                    if (lane < m) scol[warp][lane] = pcol[base + e0 + lane];
+                    asm volatile("cp.async.commit_group;\n" ::);
+                    asm volatile("cp.async.wait_group 0;\n" ::);
+                }
+                __syncwarp();
+#pragma unroll 2
+                for (int q = slot; q < m; q += 4) {
+                    const int j = scol[warp][q];
+                    double x[D][4];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const double2* xp = reinterpret_cast<const double2*>(Xs + ((int64_t)D * j + c) * b);
+                        const double2 u = xp[0], v = xp[1];
+                        x[c][0] = u.x; x[c][1] = u.y; x[c][2] = v.x; x[c][3] = v.y;
+                    }
+                    const double2* bp = reinterpret_cast<const double2*>(&sblk[warp][q * E]);
+                    double h[E];
+#pragma unroll
+                    for (int w = 0; w < E / 2; ++w) { const double2 u = bp[w]; h[2 * w] = u.x; h[2 * w + 1] = u.y; }
+#pragma unroll
+                    for (int a = 0; a < R; ++a)
+#pragma unroll
+                        for (int c = 0; c < D; ++c)
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) acc[a][cc] = fma(h[a * D + c], x[c][cc], acc[a][cc]);
+                }
+            }
+            // combine the four contact slots
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    double v = acc[a][cc];
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    acc[a][cc] = v;
+                }
+            // slot q writes rows q, q+4 of the pair (each row: 8 lanes x 32 B contiguous)
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                if ((a & 3) != slot) continue;
+                const int64_t r = (int64_t)D * 2 * t + a;
+                if (r >= N) continue;
+                const int64_t idx = (s * N + r) * b + c0;
+                double v[4] = {acc[a][0], acc[a][1], acc[a][2], acc[a][3]};
+                if (coef) {
+                    const double2* xp = reinterpret_cast<const double2*>(X + idx);
+                    const double2 u = xp[0], w2 = xp[1];
+                    const double xo[4] = {u.x, u.y, w2.x, w2.y};
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) v[cc] = alpha * (v[cc] - cshift * xo[cc]);
+                    if (W && beta != 0.0) {
+                        const double2* wp = reinterpret_cast<const double2*>(W + idx);
+                        const double2 p = wp[0], q2 = wp[1];
+                        v[0] -= beta * p.x; v[1] -= beta * p.y; v[2] -= beta * q2.x; v[3] -= beta * q2.y;
+                    }
+                }
+                double2* yp = reinterpret_cast<double2*>(Y + idx);
+                yp[0] = make_double2(v[0], v[1]);
+                yp[1] = make_double2(v[2], v[3]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+size_t paired_capacity(int B, int n, int64_t P) { return (size_t)P + 2 * (size_t)B * ((n + 1) / 2); }
+
+int build_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
+                 const double* diag, int32_t* pcount, int32_t* pcol, double* pblk, cudaStream_t st) {
+    const int np = (n + 1) / 2;
+    const int64_t total = (int64_t)B * np;
+    const unsigned grid = (unsigned)ceil_div(total, 128);
+    if (D == 3) pair_rows_kernel<3><<<grid, 128, 0, st>>>(n, np, total, rowptr, col, offdiag, diag, pcount, pcol, pblk);
+    else if (D == 1) pair_rows_kernel<1><<<grid, 128, 0, st>>>(n, np, total, rowptr, col, offdiag, diag, pcount, pcol, pblk);
+    else return SCB_ERR_INVALID;
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const int32_t* pcol,
+                const double* pblk, const double* X, const double* W, double* Y, int b, const double* coef,
+                int coef_stride, const int32_t* done, cudaStream_t st) {
+    if (b != 32 && b != 64) return SCB_ERR_UNSUPPORTED;
+    const int np = (n + 1) / 2;
+    const int64_t total = (int64_t)B * np;
+    int per_cta = (int)ceil_div(total, 4 * kNumSM);
+    per_cta = per_cta < kPairWarps ? kPairWarps : (per_cta > 256 ? 256 : per_cta);
+    if (per_cta > np) per_cta = np;
+    dim3 grid((unsigned)ceil_div(np, per_cta), (unsigned)B);
+    if (D == 3) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(spmm_paired_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
+            configured = true;
+        }
+        spmm_paired_kernel<3><<<grid, kPairWarps * 32, 0, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W, Y,
+                                                              coef, coef_stride, done);
+    } else if (D == 1) {
+        spmm_paired_kernel<1><<<grid, kPairWarps * 32, 0, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W, Y,
+                                                              coef, coef_stride, done);
+    } else {
+        return SCB_ERR_INVALID;
+    }
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" size_t scb_paired_bytes(int D, int B, int n, int64_t P, size_t* count_off, size_t* col_off,
+                                   size_t* blk_off) {
+    Arena ar(nullptr, 0);
+    const size_t cap = paired_capacity(B, n, P);
+    const size_t o0 = ar.off; ar.take<int32_t>((size_t)B * ((n + 1) / 2));
+    const size_t o1 = ar.off; ar.take<int32_t>(cap);
+    const size_t o2 = ar.off; ar.take<double>(cap * 2 * D * D);
+    if (count_off) *count_off = o0;
+    if (col_off) *col_off = o1;
+    if (blk_off) *blk_off = o2;
+    return ar.off + 256;
+}
+
+extern "C" int scb_paired_build(int D, int B, int n, int64_t P, const int64_t* rowptr, const int32_t* col,
+                                const double* offdiag, const double* diag, void* paired, void* stream) {
+    if (!rowptr || !col || !offdiag || !diag || !paired) return SCB_ERR_INVALID;
+    size_t o0, o1, o2;
+    scb_paired_bytes(D, B, n, P, &o0, &o1, &o2);
+    char* base = static_cast<char*>(paired);
+    return build_paired(D, B, n, rowptr, col, offdiag, diag, (int32_t*)(base + o0), (int32_t*)(base + o1),
+                        (double*)(base + o2), as_stream(stream));
+}
+
+extern "C" int scb_spmm_paired(int D, int B, int n, int64_t P, const int64_t* rowptr, const void* paired,
+                               const double* X, double* Y, int b, void* stream) {
+    if (!rowptr || !paired || !X || !Y) return SCB_ERR_INVALID;
+    size_t o0, o1, o2;
+    scb_paired_bytes(D, B, n, P, &o0, &o1, &o2);
+    const char* base = static_cast<const char*>(paired);
+    return spmm_paired(D, B, n, rowptr, (const int32_t*)(base + o0), (const int32_t*)(base + o1),
+                       (const double*)(base + o2), X, nullptr, Y, b, nullptr, 0, nullptr, as_stream(stream));
+}

@@ -15,6 +15,12 @@ struct EigState {
 int spmm_cheb(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
               const double* diag, const double* X, const double* W, double* Y, int b, const double* coef,
               int coef_stride, const int32_t* done, cudaStream_t st);
+size_t paired_capacity(int B, int n, int64_t P);
+int build_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
+                 const double* diag, int32_t* pcount, int32_t* pcol, double* pblk, cudaStream_t st);
+int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const int32_t* pcol,
+                const double* pblk, const double* X, const double* W, double* Y, int b, const double* coef,
+                int coef_stride, const int32_t* done, cudaStream_t st);
 int gram(int B, int64_t N, int b, const double* A, const double* Bm, double* G, const int32_t* done, cudaStream_t st);
 int small_rr(int B, int b, const double* S, const double* T, double* theta, double* C, const int32_t* done,
              int mode, cudaStream_t st, int nact = 0);

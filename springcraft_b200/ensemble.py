@@ -26,7 +26,7 @@ def _patch_of(ff, n, keep):
     return _patch_struct(ff, n, keep)
 
 
-def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=1e-10, return_modes=False,
+def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, return_modes=False,
                  pinned_out=None):
     """ANM/GNM of B conformations: coords (B, n, 3) host array (float64).
 
@@ -65,7 +65,7 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=1e-10, 
     return EnsembleResult(eig, msf, modes, int(npairs.value), status == 0)
 
 
-def enm_ensemble_device(xyz_soa, force_field, k=20, kind="anm", masses=None, tol=1e-10, out=None):
+def enm_ensemble_device(xyz_soa, force_field, k=20, kind="anm", masses=None, tol=3e-9, out=None):
     """Same path with DEVICE buffers: xyz_soa is a (B, 3, n) float64 cuda tensor.
     Returns (eigval (B,k), msf (B,n), iters (B,), n_pairs, converged); all tensors stay in HBM."""
     import torch

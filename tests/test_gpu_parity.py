@@ -197,6 +197,25 @@ def test_force_constant_method(structures):
 
 
 # --------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("D", [1, 3])
+@pytest.mark.parametrize("shape", [(1, 257, 32), (3, 300, 32), (70, 120, 32), (2, 301, 64), (1, 2500, 32)])
+def test_spmm_kernels_vs_dense(D, shape):
+    """Both SpMM kernels (row-per-warp and row-paired) against the dense product."""
+    import torch
+    from springcraft_b200._engine import DeviceModel
+    B, n, b = shape
+    rng = np.random.default_rng(B * 1000 + n)
+    base = orc.synthetic_chain(n, seed=2)
+    coords = base[None] + rng.normal(0, 0.4, size=(B, n, 3))
+    model = DeviceModel(coords, sc.HinsenForceField(11.0), D, masses=rng.uniform(50, 200, n))
+    dense = model.dense()
+    X = torch.from_numpy(rng.normal(size=(B, D * n, b))).cuda()
+    want = torch.bmm(dense, X).cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(model.spmm(X).cpu().numpy() - want).max() <= 1e-13 * scale
+    assert np.abs(model.spmm_paired(X).cpu().numpy() - want).max() <= 1e-13 * scale
+
+
 @pytest.mark.parametrize("key", ["invariant7", "invariant13", "hinsen", "e_anm", "sd_enm", "pfree"])
 def test_1l2y_full_spectrum(structures, key):
     ref = golden("ref_1l2y.npz")
