@@ -186,6 +186,8 @@ def ref_two_chain():
         pf = springcraft.PatchedForceField(ff, contact_pair_off=pair_off, contact_pair_on=pair_on,
                                            force_constants=fcs)
         out[f"{key}_patched/kirchhoff"], _ = springcraft.compute_kirchhoff(atoms.coord, pf)
+    for key in ("e_anm", "sd_enm", "s_enm_10"):
+        out[f"{key}/interaction_matrix"] = FF_BUILDERS[key](atoms).interaction_matrix
     # shifted second chain so that Hessians are finite (no zero distances)
     shifted = atoms.copy()
     shifted.coord[20:] += np.array([4.0, 3.0, -2.5], dtype=np.float32)

@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference interface: constructors, properties and
+error behaviour (no GPU needed).  Mirrors tests/test_forcefield.py of the
+reference where the logic lives on the host."""
+import numpy as np
+import pytest
+
+import springcraft_b200 as sc
+from springcraft_b200 import forcefield as ffm
+from .conftest import golden
+
+
+@pytest.fixture
+def atoms():
+    """The reference's fixture (test_forcefield.py:14-30): two overlapping chains."""
+    ref = golden("ref_two_chain.npz")
+    return sc.AtomArray(ref["coord"], ref["res_name"], ref["chain_id"], ref["res_id"])
+
+
+def test_flat_namespace():
+    for name in ("ANM", "GNM", "ForceField", "PatchedForceField", "InvariantForceField", "HinsenForceField",
+                 "ParameterFreeForceField", "TabulatedForceField", "compute_kirchhoff", "compute_hessian"):
+        assert hasattr(sc, name)
+    for name in ("eigen", "frequencies", "mean_square_fluctuation", "bfactor", "dcc", "normal_mode",
+                 "linear_response", "prs", "effector_sensor"):
+        assert hasattr(sc.nma, name)
+    assert sc.__reference_version__ == "0.3.0"
+
+
+def test_forcefield_interface_defaults():
+    class Mine(sc.ForceField):
+        def force_constant(self, atom_i, atom_j, sq_distance):
+            return np.ones(len(atom_i))
+    ff = Mine()
+    assert ff.cutoff_distance is None and ff.contact_shutdown is None and ff.contact_pair_off is None
+    assert ff.contact_pair_on is None and ff.natoms is None
+    with pytest.raises(TypeError):
+        sc.ForceField()          # abstract
+
+
+def test_invariant_needs_cutoff():
+    with pytest.raises(ValueError):
+        sc.InvariantForceField(None)
+    assert sc.InvariantForceField(7).cutoff_distance == 7
+    assert sc.HinsenForceField().cutoff_distance is None
+    assert sc.ParameterFreeForceField(9.5).cutoff_distance == 9.5
+
+
+def test_tabulated_homogeneous_interaction_matrix(atoms):
+    """test_forcefield.py:117-151."""
+    ff = sc.TabulatedForceField(atoms, 1, 2, 3, None)
+    assert ff.interaction_matrix.shape[2] == 1 and ff.interaction_matrix.dtype == np.float32
+    m = ff.interaction_matrix[:, :, 0]
+    assert np.allclose(m, m.T)
+    n = len(atoms)
+    for i in range(n):
+        for j in range(i, n):
+            if i == j:
+                assert m[i, j] == 0
+            elif j == i + 1 and atoms.chain_id[i] == atoms.chain_id[j]:
+                assert m[i, j] == 1
+            elif atoms.chain_id[i] == atoms.chain_id[j]:
+                assert m[i, j] == 2
+            else:
+                assert m[i, j] == 3
+    assert ff.natoms == 40 and ff.cutoff_distance is None
+    assert ff.interaction_matrix is ff.interaction_matrix  # returned by reference
+
+
+def test_tabulated_inhomogeneous_interaction_matrix(atoms):
+    """test_forcefield.py:154-208."""
+    mapping = np.array([ffm.AA_TO_INDEX[aa] for aa in atoms.res_name])
+    np.random.seed(0)
+    triu = np.triu(np.random.rand(3, 20, 20))
+    bonded, intra, inter = triu + np.transpose(triu, (0, 2, 1))
+    m = sc.TabulatedForceField(atoms, bonded, intra, inter, None).interaction_matrix[:, :, 0]
+    n = len(atoms)
+    for i in range(n):
+        for j in range(i, n):
+            if i == j:
+                want = 0
+            elif j == i + 1 and atoms.chain_id[i] == atoms.chain_id[j]:
+                want = bonded[mapping[i], mapping[j]]
+            elif atoms.chain_id[i] == atoms.chain_id[j]:
+                want = intra[mapping[i], mapping[j]]
+            else:
+                want = inter[mapping[i], mapping[j]]
+            assert m[i, j] == pytest.approx(want)
+
+
+@pytest.mark.parametrize("key", ["e_anm", "sd_enm", "s_enm_10"])
+def test_preset_interaction_matrix_equals_reference(atoms, key):
+    """The lazily built (n,n,k) table is bit-identical to the reference's constructor output."""
+    ref = golden("ref_two_chain.npz")
+    ff = getattr(sc.TabulatedForceField, key)(atoms)
+    assert np.array_equal(ff.interaction_matrix, ref[f"{key}/interaction_matrix"])
+    assert ff.cutoff_distance == {"e_anm": 13.0, "sd_enm": 16.5, "s_enm_10": 10.0}[key]
+
+
+@pytest.mark.parametrize(
+    "shape, n_edges, is_valid",
+    [[(), None, True], [(), 1, True], [(), 10, True], [(10,), None, False], [(10,), 1, False],
+     [(9,), 10, False], [(10,), 10, True], [(1,), None, True], [(20, 1), 1, False], [(20, 30), 1, False],
+     [(1, 20), 1, False], [(30, 20), 1, False], [(20, 20), 1, True], [(20, 20), None, True],
+     [(20, 20), 10, True], [(20, 1, 10), 10, False], [(20, 30, 10), 10, False], [(1, 20, 10), 10, False],
+     [(30, 20, 10), 10, False], [(20, 20, 10), 10, True], [(20, 20, 1), 1, True], [(20, 20, 1), None, True],
+     [(20, 20, 10), 9, False]],
+)
+def test_tabulated_input_shapes(atoms, shape, n_edges, is_valid):
+    """test_forcefield.py:277-320."""
+    fc = np.ones(shape) if shape != () else 1
+    edges = np.arange(n_edges) if n_edges is not None else None
+    if is_valid:
+        ff = sc.TabulatedForceField(atoms, fc, fc, fc, edges)
+        assert ff.interaction_matrix.shape == (40, 40, n_edges if n_edges is not None else 1)
+    else:
+        with pytest.raises(IndexError):
+            sc.TabulatedForceField(atoms, fc, fc, fc, edges)
+
+
+@pytest.mark.parametrize("name", ["s_enm_10", "s_enm_13", "d_enm", "sd_enm", "e_anm", "e_anm_mj", "e_anm_ke"])
+def test_presets_instantiate(atoms, name):
+    ff = getattr(sc.TabulatedForceField, name)(atoms)
+    assert ff.natoms == 40 and ff._bonded.dtype == np.float32
+
+
+def test_tabulated_errors(atoms):
+    with pytest.raises(TypeError):
+        sc.TabulatedForceField(atoms.coord, 1, 1, 1, 7.0)
+    bad = atoms.copy()
+    bad.atom_name = np.array(["CB"] * 40)
+    with pytest.raises(sc.BadStructureError):
+        sc.TabulatedForceField(bad, 1, 1, 1, 7.0)
+    with pytest.raises(ValueError):   # unsorted edges
+        sc.TabulatedForceField(atoms, 1, 1, 1, np.array([5.0, 4.0]))
+    asym = np.ones((20, 20))
+    asym[0, 1] = 2
+    with pytest.raises(ValueError):
+        sc.TabulatedForceField(atoms, asym, 1, 1, 7.0)
+    with pytest.raises(IndexError):
+        sc.TabulatedForceField(atoms, np.nan, 1, 1, 7.0)
+
+
+def test_patched_forcefield_checks(atoms):
+    base = sc.TabulatedForceField(atoms, 1, 1, 1, 7.0)
+    with pytest.raises(TypeError):
+        sc.PatchedForceField(base, contact_pair_on=np.array([[0, 5]]))
+    with pytest.raises(IndexError):
+        sc.PatchedForceField(base, contact_pair_on=np.array([[0, 5]]), force_constants=np.array([1.0, 2.0]))
+    with pytest.raises(IndexError):
+        sc.PatchedForceField(base, contact_shutdown=np.array([40]))
+    p1 = sc.PatchedForceField(base, contact_shutdown=np.array([1, 2]), contact_pair_off=np.array([[0, 1]]),
+                              contact_pair_on=np.array([[0, 30]]), force_constants=np.array([4.0]))
+    p2 = sc.PatchedForceField(p1, contact_shutdown=np.array([3]), contact_pair_off=np.array([[5, 6]]),
+                              contact_pair_on=np.array([[7, 8]]), force_constants=np.array([2.0]))
+    assert p2.natoms == 40 and p2.cutoff_distance == 7.0
+    assert p2.contact_shutdown.tolist() == [3, 1, 2]
+    assert p2.contact_pair_off.tolist() == [[5, 6], [0, 1]]
+    assert p2.contact_pair_on.tolist() == [[7, 8], [0, 30]]
+
+
+def test_enm_constructor_errors(atoms):
+    ff = sc.InvariantForceField(7.0)
+    with pytest.raises(IndexError):
+        sc.ANM(atoms, ff, masses=np.ones(3))
+    with pytest.raises(ValueError):
+        sc.GNM(atoms, ff, masses=np.zeros(40))
+    with pytest.raises(TypeError):
+        sc.ANM(atoms.coord, ff, masses=True)
+    anm = sc.ANM(atoms, ff, masses=True)
+    assert anm.masses.shape == (40,) and np.all(anm.masses > 50)
+    assert sc.ANM(atoms, ff).masses is None
+    assert sc.GNM(atoms, ff, masses=np.arange(1, 41))._masses.dtype == float
+    with pytest.raises(IndexError):
+        anm.hessian = np.zeros((5, 5))
+    with pytest.raises(IndexError):
+        anm.covariance = np.zeros((5, 5))
+    g = sc.GNM(atoms, ff)
+    with pytest.raises(ValueError):
+        g.kirchhoff = np.zeros((5, 5))
+    with pytest.raises(ValueError):
+        sc.nma.eigen("not an enm")
+    with pytest.raises(ValueError):
+        sc.nma.linear_response(g, np.zeros((40, 3)))
+    with pytest.raises(ValueError):
+        sc.nma.normal_mode(g, 6, 1.0, 4)
+    with pytest.raises(ValueError):
+        sc.nma.prs(g)
+
+
+def test_user_set_matrix_is_returned_by_reference(atoms):
+    anm = sc.ANM(atoms, sc.InvariantForceField(7.0))
+    H = np.eye(120)
+    anm.hessian = H
+    assert anm.hessian is H and anm._covariance is None and not anm._has_model()
+    C = np.eye(120) * 2
+    anm.covariance = C
+    assert anm.covariance is C and anm._matrix is None
+
+
+def test_effector_sensor_matches_reference_formula():
+    rng = np.random.default_rng(0)
+    m = rng.random((7, 7))
+    eff, sens = sc.nma.effector_sensor(m)
+    w = 1 - np.eye(7)
+    assert np.allclose(eff, (m * w).sum(1) / 6) and np.allclose(sens, (m * w).sum(0) / 6)
+
+
+def test_atom_array_container():
+    a = sc.AtomArray(np.zeros((3, 3)), res_name=["ALA", "GLY", "TRP"], chain_id=["A", "A", "B"], res_id=[1, 2, 1])
+    assert a.array_length() == 3 and len(a[1:]) == 2 and len(a + a) == 6
+    assert (a[a.chain_id == "A"].res_name == ["ALA", "GLY"]).all()
+    with pytest.raises(ValueError):
+        sc.AtomArray(np.zeros((3, 2)))
+    with pytest.raises(IndexError):
+        sc.AtomArray(np.zeros((3, 3)), res_name=["ALA"])
