@@ -8,7 +8,8 @@
 // ~85 % of their contacts) are merged into one list of (2D x D) blocks, the
 // diagonal blocks folded in, and the warp is split into 4 contact slots x 8
 // lanes x 4 columns:
-//   * an X row segment is loaded once (LDG.128 x2 per lane) and used for both
+//   * an X row segment is loaded once (LDG.128 x2 per lane, each instruction covering
+//     128 contiguous bytes per slot = full 32-byte sectors) and used for both
 //     block rows and 4 columns  -> 6 wavefronts per merged contact;
 //   * block values are read as LDS.128 with 4 distinct addresses per
 //     instruction (conflict free: 144-byte entries) -> 2.25 wavefronts;
@@ -94,6 +95,31 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
 // ---------------------------------------------------------------------------
 // Y = alpha (H X - c X) - beta W   on the paired format; b = 32 * ncg columns
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
+
+template <int D>
+struct PairStage {
+    static constexpr int E = 2 * D * D;
+    double blk[kPairChunk * E];
+    int32_t col[kPairChunk];
+};
+
+// stage `m` merged contacts starting at entry `first` into `st` (asynchronously)
+template <int D>
+__device__ __forceinline__ void stage_chunk(PairStage<D>* st, const double* __restrict__ pblk,
+                                            const int32_t* __restrict__ pcol, int64_t first, int m, int lane) {
+    constexpr int E = 2 * D * D;
+    const char* src = reinterpret_cast<const char*>(pblk + first * E);
+    char* dst = reinterpret_cast<char*>(st->blk);
+    const int chunks = m * E / 2;  // 16-byte pieces
+    for (int q = lane; q < chunks; q += 32) cp_async_16(dst + 16 * q, src + 16 * q);
+    if (lane < m) cp_async_4(&st->col[lane], pcol + first + lane);
+    asm volatile("cp.async.commit_group;\n" ::);
+}
+
 template <int D>
 __global__ void __launch_bounds__(kPairWarps * 32, 1)
 spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __restrict__ rowptr,
@@ -104,13 +130,13 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
     constexpr int DD = D * D;
     constexpr int E = 2 * DD;            // doubles per merged contact (18 or 2)
     constexpr int R = 2 * D;             // rows per pair (6 or 2)
-    __shared__ __align__(16) double sblk[kPairWarps][kPairChunk * E];
-    __shared__ int32_t scol[kPairWarps][kPairChunk];
+    extern __shared__ __align__(16) unsigned char pair_smem[];
     const int64_t s = blockIdx.y;
     if (done && done[s]) return;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int slot = lane >> 3, l8 = lane & 7;
+    PairStage<D>* stage = reinterpret_cast<PairStage<D>*>(pair_smem) + 2 * warp;  // double buffer per warp
     const int64_t N = (int64_t)D * n;
     double alpha = 1.0, cshift = 0.0, beta = 0.0;
     if (coef) {
@@ -120,52 +146,77 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
     const int t0 = blockIdx.x * pairs_per_cta;
     const int t1 = min(np, t0 + pairs_per_cta);
     const int ncg = b >> 5;
+    const int rowlen = D * b;            // doubles between the X rows of consecutive nodes
     for (int t = t0 + warp; t < t1; t += kPairWarps) {
         const int64_t g = s * np + t;
         const int64_t base = rowptr[s * n + 2 * t] + 2 * g;
         const int cnt = pcount[g];
+        const int nchunk = (cnt + kPairChunk - 1) / kPairChunk;
         for (int cg = 0; cg < ncg; ++cg) {
-            const int c0 = cg * 32 + 4 * l8;
+            const int c0 = cg * 32 + 2 * l8;  // columns c0, c0+1, c0+16, c0+17
             const double* Xs = X + s * N * b + c0;
             double acc[R][4];
 #pragma unroll
             for (int a = 0; a < R; ++a)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) acc[a][cc] = 0.0;
-            for (int e0 = 0; e0 < cnt; e0 += kPairChunk) {
+            __syncwarp();
+            if (nchunk > 0) stage_chunk<D>(&stage[0], pblk, pcol, base, min(kPairChunk, cnt), lane);
+            for (int ch = 0; ch < nchunk; ++ch) {
+                const int e0 = ch * kPairChunk;
                 const int m = min(kPairChunk, cnt - e0);
-                __syncwarp();
-                {   // stage m merged contacts: E*8 bytes each, 16-byte chunks, coalesced
-                    const char* src = reinterpret_cast<const char*>(pblk + (base + e0) * E);
-                    char* dst = reinterpret_cast<char*>(&sblk[warp][0]);
-                    const int chunks = m * E / 2;
-                    for (int q = lane; q < chunks; q += 32) cp_async_16(dst + 16 * q, src + 16 * q);
-                    if (lane < m) scol[warp][lane] = pcol[base + e0 + lane];
-                    asm volatile("cp.async.commit_group;\n" ::);
+                if (ch + 1 < nchunk) {
+                    stage_chunk<D>(&stage[(ch + 1) & 1], pblk, pcol, base + e0 + kPairChunk,
+                                   min(kPairChunk, cnt - e0 - kPairChunk), lane);
+                    asm volatile("cp.async.wait_group 1;\n" ::);
+                } else {
                     asm volatile("cp.async.wait_group 0;\n" ::);
                 }
                 __syncwarp();
-#pragma unroll 2
-                for (int q = slot; q < m; q += 4) {
-                    const int j = scol[warp][q];
-                    double x[D][4];
+                const PairStage<D>* cur = &stage[ch & 1];
+                // Two register sets of X rows (xa, xb): the gathers of the next contact are issued
+                // before the 72 DFMA of the current one, so their L1/L2 latency is covered.
+                double xa[D][4], xb[D][4];
+                auto gather = [&](double (&x)[D][4], int q) {
+                    const double* xr = Xs + (int64_t)cur->col[q] * rowlen;
 #pragma unroll
                     for (int c = 0; c < D; ++c) {
-                        const double2* xp = reinterpret_cast<const double2*>(Xs + ((int64_t)D * j + c) * b);
-                        const double2 u = xp[0], v = xp[1];
+                        const double2 u = __ldg(reinterpret_cast<const double2*>(xr + c * b));
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(xr + c * b + 16));
                         x[c][0] = u.x; x[c][1] = u.y; x[c][2] = v.x; x[c][3] = v.y;
                     }
-                    const double2* bp = reinterpret_cast<const double2*>(&sblk[warp][q * E]);
-                    double h[E];
+                };
+                auto apply = [&](const double (&x)[D][4], int q) {
+                    const double2* bp = reinterpret_cast<const double2*>(&cur->blk[q * E]);
 #pragma unroll
-                    for (int w = 0; w < E / 2; ++w) { const double2 u = bp[w]; h[2 * w] = u.x; h[2 * w + 1] = u.y; }
-#pragma unroll
-                    for (int a = 0; a < R; ++a)
+                    for (int a = 0; a < R; ++a) {
+                        double h[D];
+                        if (D == 3) {
+                            const int o = a * 3;  // elements o .. o+2 of the 18-double entry
+                            const double2 u = bp[o >> 1];
+                            const double2 v = bp[(o >> 1) + 1];
+                            if (o & 1) { h[0] = u.y; h[1] = v.x; h[2] = v.y; }
+                            else { h[0] = u.x; h[1] = u.y; h[2] = v.x; }
+                        } else {
+                            const double2 u = bp[0];
+                            h[0] = a ? u.y : u.x;
+                        }
 #pragma unroll
                         for (int c = 0; c < D; ++c)
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) acc[a][cc] = fma(h[a * D + c], x[c][cc], acc[a][cc]);
-                }
+                            for (int cc = 0; cc < 4; ++cc) acc[a][cc] = fma(h[c], x[c][cc], acc[a][cc]);
+                    }
+                };
+                // this slot owns contacts slot, slot+4, slot+8, slot+12 of the chunk
+                if (slot < m) gather(xa, slot);
+                if (slot + 4 < m) gather(xb, slot + 4);
+                if (slot < m) apply(xa, slot);
+                if (slot + 8 < m) gather(xa, slot + 8);
+                if (slot + 4 < m) apply(xb, slot + 4);
+                if (slot + 12 < m) gather(xb, slot + 12);
+                if (slot + 8 < m) apply(xa, slot + 8);
+                if (slot + 12 < m) apply(xb, slot + 12);
+                __syncwarp();  // buffer (ch & 1) is refilled two chunks later
             }
             // combine the four contact slots
 #pragma unroll
@@ -187,19 +238,19 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
                 double v[4] = {acc[a][0], acc[a][1], acc[a][2], acc[a][3]};
                 if (coef) {
                     const double2* xp = reinterpret_cast<const double2*>(X + idx);
-                    const double2 u = xp[0], w2 = xp[1];
+                    const double2 u = xp[0], w2 = xp[8];
                     const double xo[4] = {u.x, u.y, w2.x, w2.y};
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) v[cc] = alpha * (v[cc] - cshift * xo[cc]);
                     if (W && beta != 0.0) {
                         const double2* wp = reinterpret_cast<const double2*>(W + idx);
-                        const double2 p = wp[0], q2 = wp[1];
+                        const double2 p = wp[0], q2 = wp[8];
                         v[0] -= beta * p.x; v[1] -= beta * p.y; v[2] -= beta * q2.x; v[3] -= beta * q2.y;
                     }
                 }
                 double2* yp = reinterpret_cast<double2*>(Y + idx);
                 yp[0] = make_double2(v[0], v[1]);
-                yp[1] = make_double2(v[2], v[3]);
+                yp[8] = make_double2(v[2], v[3]);
             }
         }
     }
@@ -233,16 +284,18 @@ int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcoun
     if (per_cta > np) per_cta = np;
     dim3 grid((unsigned)ceil_div(np, per_cta), (unsigned)B);
     if (D == 3) {
+        const size_t smem = sizeof(PairStage<3>) * 2 * kPairWarps;
         static bool configured = false;
         if (!configured) {
-            cudaFuncSetAttribute(spmm_paired_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
+            SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
-        spmm_paired_kernel<3><<<grid, kPairWarps * 32, 0, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W, Y,
-                                                              coef, coef_stride, done);
+        spmm_paired_kernel<3><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W,
+                                                                 Y, coef, coef_stride, done);
     } else if (D == 1) {
-        spmm_paired_kernel<1><<<grid, kPairWarps * 32, 0, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W, Y,
-                                                              coef, coef_stride, done);
+        const size_t smem = sizeof(PairStage<1>) * 2 * kPairWarps;
+        spmm_paired_kernel<1><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W,
+                                                                 Y, coef, coef_stride, done);
     } else {
         return SCB_ERR_INVALID;
     }
