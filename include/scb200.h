@@ -160,10 +160,9 @@ int scb_spmm(int D, int B, int n, const int64_t *rowptr, const int32_t *col,
              int b, void *stream);
 /* Row-paired operator used by the eigensolver (two consecutive block rows merged
  * into (2D x D) blocks, diagonal folded in; spmm_paired.cu).  `paired` is one
- * device buffer of scb_paired_bytes(); the three offsets (may be NULL) locate the
- * per-pair counts, merged column indices and merged blocks inside it. */
-size_t scb_paired_bytes(int D, int B, int n, int64_t P, size_t *count_off, size_t *col_off,
-                        size_t *blk_off);
+ * device buffer of scb_paired_bytes(); the two offsets (may be NULL) locate the
+ * per-pair counts and the merged-contact records {blocks, column} inside it. */
+size_t scb_paired_bytes(int D, int B, int n, int64_t P, size_t *count_off, size_t *entry_off);
 int scb_paired_build(int D, int B, int n, int64_t P, const int64_t *rowptr, const int32_t *col,
                      const double *offdiag, const double *diag, void *paired, void *stream);
 int scb_spmm_paired(int D, int B, int n, int64_t P, const int64_t *rowptr, const void *paired,

@@ -194,7 +194,7 @@ class DeviceModel:
         """Row-paired copy of the operator (built once, cached)."""
         torch = _torch()
         if getattr(self, "_paired", None) is None:
-            nbytes = self.handle.scb_paired_bytes(self.D, self.B, self.n, self.P, None, None, None)
+            nbytes = self.handle.scb_paired_bytes(self.D, self.B, self.n, self.P, None, None)
             buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
             _lib.check(self.handle.scb_paired_build(self.D, self.B, self.n, self.P, _lib.ptr(self.rowptr),
                                                     _lib.ptr(self.col), _lib.ptr(self.offdiag), _lib.ptr(self.diag),

@@ -78,7 +78,7 @@ SIGNATURES = {
     "scb_densify": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "scb_assemble_dense_allpairs": (_I, [_I, _P, _I, C.POINTER(FFDesc), _P, _I, _I, _P, _P]),
     "scb_spmm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
-    "scb_paired_bytes": (_SZ, [_I, _I, _I, _I64, _P, _P, _P]),
+    "scb_paired_bytes": (_SZ, [_I, _I, _I, _I64, _P, _P]),
     "scb_paired_build": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _P, _P]),
     "scb_spmm_paired": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _I, _P]),
     "scb_rigid_basis": (_I, [_I, _P, _I, _I, _P, _P, _P]),

@@ -15,13 +15,16 @@
 
 namespace scb {
 
+constexpr int kLanczosSteps = 10;  // column-wise Lanczos steps of the spectrum-bound estimator
+
 struct EigWork {
     double *A, *Bf, *Cf, *HX;    // block vectors [B][N][b]; A is the canonical basis (caller's X)
     double *S, *T, *Cm, *theta, *rn2, *P, *coef;
+    double *lz_alpha, *lz_beta2;  // Lanczos coefficients [steps][B][b]
     EigState* state;
     int32_t *done, *n_active;
-    int32_t *pcount, *pcol;   // row-paired operator (spmm_paired.cu)
-    double* pblk;
+    int32_t* pcount;          // row-paired operator (spmm_paired.cu)
+    char* pent;
 };
 
 static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, int degree_cap, double* X,
@@ -39,13 +42,14 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
     w->rn2 = ar.take<double>((size_t)B * b);
     w->P = ar.take<double>((size_t)B * 8 * b);
     w->coef = ar.take<double>((size_t)B * degree_cap * 3);
+    w->lz_alpha = ar.take<double>((size_t)kLanczosSteps * B * b);
+    w->lz_beta2 = ar.take<double>((size_t)kLanczosSteps * B * b);
     w->state = ar.take<EigState>(B);
     w->done = ar.take<int32_t>(B);
     w->n_active = ar.take<int32_t>(1);
     const size_t cap = paired_capacity(B, n, P);
     w->pcount = ar.take<int32_t>((size_t)B * ((n + 1) / 2));
-    w->pcol = ar.take<int32_t>(cap);
-    w->pblk = ar.take<double>(cap * 2 * D * D);
+    w->pent = ar.take<char>(cap * paired_entry_bytes(D));
     (void)nz;
     return ar.off;
 }
@@ -81,14 +85,35 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
     if (!ar.ok()) return SCB_ERR_WORKSPACE;
     const int32_t* done = w.done;
     // row-paired copy of the operator for the register-blocked SpMM
-    SCB_TRY(build_paired(D, B, n, rowptr, col, offdiag, diag, w.pcount, w.pcol, w.pblk, st));
+    SCB_TRY(build_paired(D, B, n, rowptr, col, offdiag, diag, w.pcount, w.pent, st));
     auto apply = [&](const double* Xin, const double* Win, double* Yout, const double* cf, int stride) {
-        return spmm_paired(D, B, n, rowptr, w.pcount, w.pcol, w.pblk, Xin, Win, Yout, b, cf, stride, done, st);
+        return spmm_paired(D, B, n, rowptr, w.pcount, w.pent, Xin, Win, Yout, b, cf, stride, done, st);
     };
 
     SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
     SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
+
+    // ---- spectrum bound: column-wise Lanczos on a copy of the random block (V=Bf, Vprev=Cf, W=HX)
+    if (N > 4 * kLanczosSteps) {
+        const size_t vec_bytes = sizeof(double) * (size_t)B * N * b;
+        SCB_CUDA(cudaMemcpyAsync(w.Bf, w.A, vec_bytes, cudaMemcpyDeviceToDevice, st));
+        SCB_CUDA(cudaMemsetAsync(w.Cf, 0, vec_bytes, st));
+        SCB_TRY(coldot(B, N, b, w.Bf, w.Bf, w.rn2, st));
+        SCB_TRY(lanczos_axpy(B, N, b, 2, w.Bf, nullptr, nullptr, nullptr, nullptr, w.rn2, st));
+        for (int j = 0; j < kLanczosSteps; ++j) {
+            double* aj = w.lz_alpha + (size_t)j * B * b;
+            double* bj = w.lz_beta2 + (size_t)j * B * b;
+            const double* bprev = j > 0 ? w.lz_beta2 + (size_t)(j - 1) * B * b : nullptr;
+            SCB_TRY(apply(w.Bf, nullptr, w.HX, nullptr, 0));
+            SCB_TRY(coldot(B, N, b, w.Bf, w.HX, aj, st));
+            SCB_TRY(lanczos_axpy(B, N, b, 0, w.Bf, w.Cf, w.HX, aj, bprev, nullptr, st));
+            SCB_TRY(coldot(B, N, b, w.HX, w.HX, bj, st));
+            if (j + 1 < kLanczosSteps) SCB_TRY(lanczos_axpy(B, N, b, 1, w.Bf, w.Cf, w.HX, nullptr, nullptr, bj, st));
+        }
+        SCB_TRY(lanczos_bound(B, b, kLanczosSteps, w.lz_alpha, w.lz_beta2, w.state, st));
+        SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
+    }
 
     int32_t* h_active = nullptr;
     SCB_CUDA(cudaMallocHost(&h_active, sizeof(int32_t)));

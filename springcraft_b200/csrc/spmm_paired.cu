@@ -1,4 +1,4 @@
-// K3a': SpMM on a row-PAIRED block format ("BSR 2Dx D"), the tuned operator of
+// K3a': SpMM on a row-PAIRED block format ("BSR 2D x D"), the tuned operator of
 // the lowest-k eigensolver.
 //
 // ncu on the one-row-per-warp kernel (profiles/r1a) shows L1/TEX at 94 % of
@@ -8,20 +8,31 @@
 // ~85 % of their contacts) are merged into one list of (2D x D) blocks, the
 // diagonal blocks folded in, and the warp is split into 4 contact slots x 8
 // lanes x 4 columns:
-//   * an X row segment is loaded once (LDG.128 x2 per lane, each instruction covering
-//     128 contiguous bytes per slot = full 32-byte sectors) and used for both
-//     block rows and 4 columns  -> 6 wavefronts per merged contact;
+//   * an X row segment is loaded once (LDG.128 x2 per lane, each instruction
+//     covering 128 contiguous bytes per slot = full 32-byte sectors) and used
+//     for both block rows and 4 columns;
 //   * block values are read as LDS.128 with 4 distinct addresses per
-//     instruction (conflict free: 144-byte entries) -> 2.25 wavefronts;
-//   * 72 DFMA per lane and merged contact -> 9 cycles/contact on the FP64 pipe,
-//     i.e. the inner loop is FP64-bound instead of L1-bound.
-// Blocks are staged global->shared with cp.async (16-byte chunks, coalesced).
+//     instruction (conflict free: 160-byte records);
+//   * 72 DFMA per lane and merged contact.
+// A merged contact is one 160-byte record {2 DxD blocks, column index}; a chunk
+// of 16 records is staged global->shared by ONE TMA bulk copy
+// (cp.async.bulk + mbarrier, double buffered per warp), which keeps the
+// staging traffic off the LSU/L1 wavefront budget (profiles/r1c: the LDGSTS
+// staging cost ~30 % of the L1 wavefronts).
 #include "subspace.cuh"
 
 namespace scb {
 
 constexpr int kPairWarps = 16;     // warps per CTA (128 registers per thread available)
 constexpr int kPairChunk = 16;     // merged contacts staged per warp and round (4 per slot)
+
+template <int D>
+struct PairEntry {                 // one merged contact
+    double blk[2 * D * D];         // rows of residue 2t (D x D), then of residue 2t+1
+    int32_t col;                   // node index of the contact
+    int32_t pad[3];
+};
+static_assert(sizeof(PairEntry<3>) == 160 && sizeof(PairEntry<1>) == 32, "record layout");
 
 // ---------------------------------------------------------------------------
 // format conversion: CSR/BSR (D x D) -> paired.  One thread per row pair does a
@@ -33,8 +44,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 pair_rows_kernel(int n, int np, int64_t total_pairs, const int64_t* __restrict__ rowptr,
                  const int32_t* __restrict__ col, const double* __restrict__ offdiag,
-                 const double* __restrict__ diag, int32_t* __restrict__ pcount, int32_t* __restrict__ pcol,
-                 double* __restrict__ pblk) {
+                 const double* __restrict__ diag, int32_t* __restrict__ pcount, PairEntry<D>* __restrict__ pent) {
     constexpr int DD = D * D;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_pairs) return;
@@ -62,81 +72,93 @@ pair_rows_kernel(int n, int np, int64_t total_pairs, const int64_t* __restrict__
         }
         const int c = min(ca, cb);
         if (c == BIG) break;
-        double* dst = pblk + out * (2 * DD);
+        PairEntry<D>* dst = pent + out;
         if (ca == c) {
             const double* src = a_is_diag ? diag + r0 * DD : offdiag + a * DD;
 #pragma unroll
-            for (int q = 0; q < DD; ++q) dst[q] = src[q];
+            for (int q = 0; q < DD; ++q) dst->blk[q] = src[q];
             if (a_is_diag) d0 = true; else ++a;
         } else {
 #pragma unroll
-            for (int q = 0; q < DD; ++q) dst[q] = 0.0;
+            for (int q = 0; q < DD; ++q) dst->blk[q] = 0.0;
         }
         if (cb == c) {
             const double* src = b_is_diag ? diag + r1 * DD : offdiag + b * DD;
 #pragma unroll
-            for (int q = 0; q < DD; ++q) dst[DD + q] = src[q];
+            for (int q = 0; q < DD; ++q) dst->blk[DD + q] = src[q];
             if (b_is_diag) d1 = true; else ++b;
         } else {
 #pragma unroll
-            for (int q = 0; q < DD; ++q) dst[DD + q] = 0.0;
+            for (int q = 0; q < DD; ++q) dst->blk[DD + q] = 0.0;
         }
-        pcol[out] = c;
+        dst->col = c;
         ++out;
     }
     pcount[g] = (int)(out - out0);
 }
 
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+// ---------------------------------------------------------------------------
+// TMA bulk copy + mbarrier helpers (SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------
 // Y = alpha (H X - c X) - beta W   on the paired format; b = 32 * ncg columns
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
-}
-
-template <int D>
-struct PairStage {
-    static constexpr int E = 2 * D * D;
-    double blk[kPairChunk * E];
-    int32_t col[kPairChunk];
-};
-
-// stage `m` merged contacts starting at entry `first` into `st` (asynchronously)
-template <int D>
-__device__ __forceinline__ void stage_chunk(PairStage<D>* st, const double* __restrict__ pblk,
-                                            const int32_t* __restrict__ pcol, int64_t first, int m, int lane) {
-    constexpr int E = 2 * D * D;
-    const char* src = reinterpret_cast<const char*>(pblk + first * E);
-    char* dst = reinterpret_cast<char*>(st->blk);
-    const int chunks = m * E / 2;  // 16-byte pieces
-    for (int q = lane; q < chunks; q += 32) cp_async_16(dst + 16 * q, src + 16 * q);
-    if (lane < m) cp_async_4(&st->col[lane], pcol + first + lane);
-    asm volatile("cp.async.commit_group;\n" ::);
-}
-
 template <int D>
 __global__ void __launch_bounds__(kPairWarps * 32, 1)
 spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __restrict__ rowptr,
-                   const int32_t* __restrict__ pcount, const int32_t* __restrict__ pcol,
-                   const double* __restrict__ pblk, const double* __restrict__ X, const double* __restrict__ W,
-                   double* __restrict__ Y, const double* __restrict__ coef, int coef_stride,
-                   const int32_t* __restrict__ done) {
-    constexpr int DD = D * D;
-    constexpr int E = 2 * DD;            // doubles per merged contact (18 or 2)
+                   const int32_t* __restrict__ pcount, const PairEntry<D>* __restrict__ pent,
+                   const double* __restrict__ X, const double* __restrict__ W, double* __restrict__ Y,
+                   const double* __restrict__ coef, int coef_stride, const int32_t* __restrict__ done) {
     constexpr int R = 2 * D;             // rows per pair (6 or 2)
-    extern __shared__ __align__(16) unsigned char pair_smem[];
+    using Entry = PairEntry<D>;
+    extern __shared__ __align__(128) unsigned char pair_smem[];
+    Entry* stage_base = reinterpret_cast<Entry*>(pair_smem);                                  // [warps][2][chunk]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + kPairWarps * 2 * kPairChunk);   // [warps][2]
     const int64_t s = blockIdx.y;
     if (done && done[s]) return;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int slot = lane >> 3, l8 = lane & 7;
-    PairStage<D>* stage = reinterpret_cast<PairStage<D>*>(pair_smem) + 2 * warp;  // double buffer per warp
+    Entry* stage = stage_base + (size_t)warp * 2 * kPairChunk;
+    uint64_t* bar = bars + 2 * warp;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase0 = 0, phase1 = 0;     // parity of the next completion of each buffer
     const int64_t N = (int64_t)D * n;
     double alpha = 1.0, cshift = 0.0, beta = 0.0;
     if (coef) {
@@ -153,46 +175,49 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
         const int cnt = pcount[g];
         const int nchunk = (cnt + kPairChunk - 1) / kPairChunk;
         for (int cg = 0; cg < ncg; ++cg) {
-            const int c0 = cg * 32 + 2 * l8;  // columns c0, c0+1, c0+16, c0+17
+            const int c0 = cg * 32 + 2 * l8;  // this lane's columns: c0, c0+1, c0+16, c0+17
             const double* Xs = X + s * N * b + c0;
             double acc[R][4];
 #pragma unroll
             for (int a = 0; a < R; ++a)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) acc[a][cc] = 0.0;
-            __syncwarp();
-            if (nchunk > 0) stage_chunk<D>(&stage[0], pblk, pcol, base, min(kPairChunk, cnt), lane);
+            __syncwarp();  // every lane is done with both buffers
+            if (nchunk > 0 && lane == 0) {
+                const unsigned bytes = (unsigned)(min(kPairChunk, cnt) * sizeof(Entry));
+                mbar_expect_tx(&bar[0], bytes);
+                bulk_g2s(stage, pent + base, bytes, &bar[0]);
+            }
             for (int ch = 0; ch < nchunk; ++ch) {
                 const int e0 = ch * kPairChunk;
                 const int m = min(kPairChunk, cnt - e0);
-                if (ch + 1 < nchunk) {
-                    stage_chunk<D>(&stage[(ch + 1) & 1], pblk, pcol, base + e0 + kPairChunk,
-                                   min(kPairChunk, cnt - e0 - kPairChunk), lane);
-                    asm volatile("cp.async.wait_group 1;\n" ::);
-                } else {
-                    asm volatile("cp.async.wait_group 0;\n" ::);
+                const int buf = ch & 1;
+                if (ch + 1 < nchunk && lane == 0) {
+                    // one elected lane arms the barrier and launches the bulk copy of the next chunk
+                    const unsigned bytes = (unsigned)(min(kPairChunk, cnt - e0 - kPairChunk) * sizeof(Entry));
+                    mbar_expect_tx(&bar[buf ^ 1], bytes);
+                    bulk_g2s(stage + (buf ^ 1) * kPairChunk, pent + base + e0 + kPairChunk, bytes, &bar[buf ^ 1]);
                 }
-                __syncwarp();
-                const PairStage<D>* cur = &stage[ch & 1];
-                // Two register sets of X rows (xa, xb): the gathers of the next contact are issued
-                // before the 72 DFMA of the current one, so their L1/L2 latency is covered.
-                double xa[D][4], xb[D][4];
-                auto gather = [&](double (&x)[D][4], int q) {
-                    const double* xr = Xs + (int64_t)cur->col[q] * rowlen;
+                if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+                else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+                const Entry* cur = stage + buf * kPairChunk;
+                // this slot owns contacts slot, slot+4, slot+8, slot+12 of the chunk
+#pragma unroll 2
+                for (int q = slot; q < m; q += 4) {
+                    const double* xr = Xs + (int64_t)cur[q].col * rowlen;
+                    double x[D][4];
 #pragma unroll
                     for (int c = 0; c < D; ++c) {
                         const double2 u = __ldg(reinterpret_cast<const double2*>(xr + c * b));
                         const double2 v = __ldg(reinterpret_cast<const double2*>(xr + c * b + 16));
                         x[c][0] = u.x; x[c][1] = u.y; x[c][2] = v.x; x[c][3] = v.y;
                     }
-                };
-                auto apply = [&](const double (&x)[D][4], int q) {
-                    const double2* bp = reinterpret_cast<const double2*>(&cur->blk[q * E]);
+                    const double2* bp = reinterpret_cast<const double2*>(cur[q].blk);
 #pragma unroll
                     for (int a = 0; a < R; ++a) {
                         double h[D];
                         if (D == 3) {
-                            const int o = a * 3;  // elements o .. o+2 of the 18-double entry
+                            const int o = a * 3;  // elements o .. o+2 of the 18-double record
                             const double2 u = bp[o >> 1];
                             const double2 v = bp[(o >> 1) + 1];
                             if (o & 1) { h[0] = u.y; h[1] = v.x; h[2] = v.y; }
@@ -206,17 +231,8 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) acc[a][cc] = fma(h[c], x[c][cc], acc[a][cc]);
                     }
-                };
-                // this slot owns contacts slot, slot+4, slot+8, slot+12 of the chunk
-                if (slot < m) gather(xa, slot);
-                if (slot + 4 < m) gather(xb, slot + 4);
-                if (slot < m) apply(xa, slot);
-                if (slot + 8 < m) gather(xa, slot + 8);
-                if (slot + 4 < m) apply(xb, slot + 4);
-                if (slot + 12 < m) gather(xb, slot + 12);
-                if (slot + 8 < m) apply(xa, slot + 8);
-                if (slot + 12 < m) apply(xb, slot + 12);
-                __syncwarp();  // buffer (ch & 1) is refilled two chunks later
+                }
+                __syncwarp();  // buffer `buf` may be refilled by the next bulk copy
             }
             // combine the four contact slots
 #pragma unroll
@@ -228,7 +244,7 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
                     v += __shfl_xor_sync(0xffffffffu, v, 16);
                     acc[a][cc] = v;
                 }
-            // slot q writes rows q, q+4 of the pair (each row: 8 lanes x 32 B contiguous)
+            // slot q writes rows q, q+4 of the pair (each row: 8 lanes x 16 B contiguous, twice)
 #pragma unroll
             for (int a = 0; a < R; ++a) {
                 if ((a & 3) != slot) continue;
@@ -260,22 +276,45 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
 // host side
 // ---------------------------------------------------------------------------
 size_t paired_capacity(int B, int n, int64_t P) { return (size_t)P + 2 * (size_t)B * ((n + 1) / 2); }
+size_t paired_entry_bytes(int D) { return D == 3 ? sizeof(PairEntry<3>) : sizeof(PairEntry<1>); }
 
 int build_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
-                 const double* diag, int32_t* pcount, int32_t* pcol, double* pblk, cudaStream_t st) {
+                 const double* diag, int32_t* pcount, void* pent, cudaStream_t st) {
     const int np = (n + 1) / 2;
     const int64_t total = (int64_t)B * np;
     const unsigned grid = (unsigned)ceil_div(total, 128);
-    if (D == 3) pair_rows_kernel<3><<<grid, 128, 0, st>>>(n, np, total, rowptr, col, offdiag, diag, pcount, pcol, pblk);
-    else if (D == 1) pair_rows_kernel<1><<<grid, 128, 0, st>>>(n, np, total, rowptr, col, offdiag, diag, pcount, pcol, pblk);
-    else return SCB_ERR_INVALID;
+    if (D == 3)
+        pair_rows_kernel<3><<<grid, 128, 0, st>>>(n, np, total, rowptr, col, offdiag, diag, pcount,
+                                                  static_cast<PairEntry<3>*>(pent));
+    else if (D == 1)
+        pair_rows_kernel<1><<<grid, 128, 0, st>>>(n, np, total, rowptr, col, offdiag, diag, pcount,
+                                                  static_cast<PairEntry<1>*>(pent));
+    else
+        return SCB_ERR_INVALID;
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
 
-int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const int32_t* pcol,
-                const double* pblk, const double* X, const double* W, double* Y, int b, const double* coef,
-                int coef_stride, const int32_t* done, cudaStream_t st) {
+template <int D>
+static int launch_paired(dim3 grid, int n, int np, int per_cta, int b, const int64_t* rowptr, const int32_t* pcount,
+                         const void* pent, const double* X, const double* W, double* Y, const double* coef,
+                         int coef_stride, const int32_t* done, cudaStream_t st) {
+    const size_t smem = sizeof(PairEntry<D>) * 2 * kPairChunk * kPairWarps + sizeof(uint64_t) * 2 * kPairWarps;
+    static bool configured = false;
+    if (!configured) {
+        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    spmm_paired_kernel<D><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, b, rowptr, pcount,
+                                                             static_cast<const PairEntry<D>*>(pent), X, W, Y, coef,
+                                                             coef_stride, done);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const void* pent,
+                const double* X, const double* W, double* Y, int b, const double* coef, int coef_stride,
+                const int32_t* done, cudaStream_t st) {
     if (b != 32 && b != 64) return SCB_ERR_UNSUPPORTED;
     const int np = (n + 1) / 2;
     const int64_t total = (int64_t)B * np;
@@ -283,59 +322,42 @@ int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcoun
     per_cta = per_cta < kPairWarps ? kPairWarps : (per_cta > 256 ? 256 : per_cta);
     if (per_cta > np) per_cta = np;
     dim3 grid((unsigned)ceil_div(np, per_cta), (unsigned)B);
-    if (D == 3) {
-        const size_t smem = sizeof(PairStage<3>) * 2 * kPairWarps;
-        static bool configured = false;
-        if (!configured) {
-            SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        spmm_paired_kernel<3><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W,
-                                                                 Y, coef, coef_stride, done);
-    } else if (D == 1) {
-        const size_t smem = sizeof(PairStage<1>) * 2 * kPairWarps;
-        spmm_paired_kernel<1><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, b, rowptr, pcount, pcol, pblk, X, W,
-                                                                 Y, coef, coef_stride, done);
-    } else {
-        return SCB_ERR_INVALID;
-    }
-    SCB_LAUNCH_CHECK();
-    return SCB_OK;
+    if (D == 3) return launch_paired<3>(grid, n, np, per_cta, b, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
+    if (D == 1) return launch_paired<1>(grid, n, np, per_cta, b, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
+    return SCB_ERR_INVALID;
 }
 
 }  // namespace scb
 
 using namespace scb;
 
-extern "C" size_t scb_paired_bytes(int D, int B, int n, int64_t P, size_t* count_off, size_t* col_off,
-                                   size_t* blk_off) {
+extern "C" size_t scb_paired_bytes(int D, int B, int n, int64_t P, size_t* count_off, size_t* entry_off) {
     Arena ar(nullptr, 0);
     const size_t cap = paired_capacity(B, n, P);
-    const size_t o0 = ar.off; ar.take<int32_t>((size_t)B * ((n + 1) / 2));
-    const size_t o1 = ar.off; ar.take<int32_t>(cap);
-    const size_t o2 = ar.off; ar.take<double>(cap * 2 * D * D);
+    const size_t o0 = ar.off;
+    ar.take<int32_t>((size_t)B * ((n + 1) / 2));
+    const size_t o1 = ar.off;
+    ar.take<char>(cap * paired_entry_bytes(D));
     if (count_off) *count_off = o0;
-    if (col_off) *col_off = o1;
-    if (blk_off) *blk_off = o2;
+    if (entry_off) *entry_off = o1;
     return ar.off + 256;
 }
 
 extern "C" int scb_paired_build(int D, int B, int n, int64_t P, const int64_t* rowptr, const int32_t* col,
                                 const double* offdiag, const double* diag, void* paired, void* stream) {
     if (!rowptr || !col || !offdiag || !diag || !paired) return SCB_ERR_INVALID;
-    size_t o0, o1, o2;
-    scb_paired_bytes(D, B, n, P, &o0, &o1, &o2);
+    size_t o0, o1;
+    scb_paired_bytes(D, B, n, P, &o0, &o1);
     char* base = static_cast<char*>(paired);
-    return build_paired(D, B, n, rowptr, col, offdiag, diag, (int32_t*)(base + o0), (int32_t*)(base + o1),
-                        (double*)(base + o2), as_stream(stream));
+    return build_paired(D, B, n, rowptr, col, offdiag, diag, (int32_t*)(base + o0), base + o1, as_stream(stream));
 }
 
 extern "C" int scb_spmm_paired(int D, int B, int n, int64_t P, const int64_t* rowptr, const void* paired,
                                const double* X, double* Y, int b, void* stream) {
     if (!rowptr || !paired || !X || !Y) return SCB_ERR_INVALID;
-    size_t o0, o1, o2;
-    scb_paired_bytes(D, B, n, P, &o0, &o1, &o2);
+    size_t o0, o1;
+    scb_paired_bytes(D, B, n, P, &o0, &o1);
     const char* base = static_cast<const char*>(paired);
-    return spmm_paired(D, B, n, rowptr, (const int32_t*)(base + o0), (const int32_t*)(base + o1),
-                       (const double*)(base + o2), X, nullptr, Y, b, nullptr, 0, nullptr, as_stream(stream));
+    return spmm_paired(D, B, n, rowptr, (const int32_t*)(base + o0), base + o1, X, nullptr, Y, b, nullptr, 0, nullptr,
+                       as_stream(stream));
 }

@@ -431,6 +431,7 @@ __global__ void state_init_kernel(int B, const double* __restrict__ gersh, EigSt
     if (s >= B) return;
     EigState e;
     e.ub = gersh[s] * (1.0 + 1e-10) + 1e-300;
+    e.ub_safe = e.ub;
     e.lo = 0.0;
     e.a0 = 0.0;
     e.iters = 0;
@@ -462,6 +463,9 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
         if (q < k) worst = fmax(worst, r);
     }
     e.a0 = th[0];
+    // repair a too small (estimated) upper bound: after a filter pass the largest Ritz value of the block
+    // must sit far below ub; if it does not, the estimate was violated -> fall back towards the safe bound
+    if (e.iters > 1 && e.ub < e.ub_safe && th[b - 1] > 0.5 * e.ub) e.ub = fmin(e.ub_safe, 1.15 * fmax(e.ub, th[b - 1]));
     double lo = th[b - 1];
     // keep the damped interval [lo, ub] non-degenerate
     lo = fmin(lo, 0.98 * e.ub);
@@ -540,6 +544,154 @@ int gather_results(int B, int b, const double* theta, const EigState* st, double
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Spectrum upper bound: k steps of column-wise Lanczos on the block (every one of
+// the b columns is an independent Lanczos run started from a random vector).
+// The largest Ritz value over all columns under-estimates lambda_max by a few
+// percent after ~10 steps; the solver uses min(Gershgorin, 1.05 * estimate) and
+// repairs the bound if a filtered block ever shows that it was too small.
+// ---------------------------------------------------------------------------
+// out[s][c] += sum_r A[r][c] * B[r][c]
+template <int CC>
+__global__ void __launch_bounds__(256)
+coldot_kernel(int64_t N, const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ out) {
+    constexpr int BW = 32 * CC;
+    __shared__ double red[8][BW];
+    const int s = blockIdx.y;
+    const double* As = A + (int64_t)s * N * BW;
+    const double* Bs = Bm + (int64_t)s * N * BW;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    double acc[CC];
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) acc[cc] = 0.0;
+    const int64_t r0 = (int64_t)blockIdx.x * kGramRows;
+    const int64_t r1 = min(N, r0 + kGramRows);
+    for (int64_t r = r0 + warp; r < r1; r += 8)
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+            acc[cc] = fma(As[r * BW + lane + 32 * cc], Bs[r * BW + lane + 32 * cc], acc[cc]);
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) red[warp][lane + 32 * cc] = acc[cc];
+    __syncthreads();
+    for (int c = threadIdx.x; c < BW; c += 256) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w][c];
+        atomicAdd(&out[(int64_t)s * BW + c], t);
+    }
+}
+
+// mode 0: W <- W - alpha[c] V - beta_prev[c] Vprev          (alpha = dot(V,W) just computed)
+// mode 1: Vprev <- V ; V <- W / sqrt(nrm2[c])               (nrm2 = ||W||^2 just computed)
+// mode 2: V <- V / sqrt(nrm2[c])                            (normalise the start block)
+template <int CC>
+__global__ void __launch_bounds__(256)
+lanczos_axpy_kernel(int64_t N, int mode, double* __restrict__ V, double* __restrict__ Vprev, double* __restrict__ Wm,
+                    const double* __restrict__ alpha, const double* __restrict__ beta_prev,
+                    const double* __restrict__ nrm2) {
+    constexpr int BW = 32 * CC;
+    const int s = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const int64_t off = (int64_t)s * N * BW;
+    const int64_t r0 = (int64_t)blockIdx.x * kGramRows;
+    const int64_t r1 = min(N, r0 + kGramRows);
+    double a[CC], bp[CC], inv[CC];
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) {
+        const int64_t q = (int64_t)s * BW + lane + 32 * cc;
+        a[cc] = alpha ? alpha[q] : 0.0;
+        bp[cc] = beta_prev ? sqrt(fmax(beta_prev[q], 0.0)) : 0.0;
+        inv[cc] = nrm2 ? rsqrt(fmax(nrm2[q], 1e-300)) : 0.0;
+    }
+    for (int64_t r = r0 + warp; r < r1; r += 8)
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+            const int64_t idx = off + r * BW + lane + 32 * cc;
+            if (mode == 0) {
+                Wm[idx] = Wm[idx] - a[cc] * V[idx] - bp[cc] * Vprev[idx];
+            } else if (mode == 1) {
+                Vprev[idx] = V[idx];
+                V[idx] = Wm[idx] * inv[cc];
+            } else {
+                V[idx] = V[idx] * inv[cc];
+            }
+        }
+}
+
+// largest eigenvalue of each column's k x k Lanczos tridiagonal (bisection on the
+// Sturm count), max over columns -> tightened upper bound in the solver state
+__global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restrict__ alpha,
+                                     const double* __restrict__ beta2, EigState* st) {
+    // alpha[j][s][c], beta2[j][s][c] = beta_j^2 (coupling between steps j and j+1)
+    const int s = blockIdx.x;
+    const int c = threadIdx.x;
+    __shared__ double best[128];
+    double th = 0.0;
+    if (c < b) {
+        double lo = 0.0, hi = 0.0;
+        for (int j = 0; j < k; ++j) {  // Gershgorin interval of T
+            const double a = alpha[((int64_t)j * B + s) * b + c];
+            const double bl = j > 0 ? sqrt(fmax(beta2[((int64_t)(j - 1) * B + s) * b + c], 0.0)) : 0.0;
+            const double br = j < k - 1 ? sqrt(fmax(beta2[((int64_t)j * B + s) * b + c], 0.0)) : 0.0;
+            hi = (j == 0) ? a + bl + br : fmax(hi, a + bl + br);
+            lo = (j == 0) ? a - bl - br : fmin(lo, a - bl - br);
+        }
+        // bisection: number of eigenvalues < x from the signs of the LDL^T pivots
+        for (int it = 0; it < 60; ++it) {
+            const double x = 0.5 * (lo + hi);
+            int below = 0;
+            double d = 1.0;
+            for (int j = 0; j < k; ++j) {
+                const double a = alpha[((int64_t)j * B + s) * b + c];
+                const double b2 = j > 0 ? fmax(beta2[((int64_t)(j - 1) * B + s) * b + c], 0.0) : 0.0;
+                d = (a - x) - (j > 0 ? b2 / d : 0.0);
+                if (d == 0.0) d = -1e-300;
+                below += d < 0.0;
+            }
+            if (below >= k) hi = x; else lo = x;  // all k eigenvalues below x -> x is above theta_max
+        }
+        th = hi;
+    }
+    best[c] = th;
+    __syncthreads();
+    if (c == 0) {
+        double m = 0.0;
+        for (int q = 0; q < b; ++q) m = fmax(m, best[q]);
+        EigState e = st[s];
+        const double est = 1.05 * m;
+        if (est > 0.0 && est < e.ub) e.ub = est;
+        st[s] = e;
+    }
+}
+
+int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st) {
+    SCB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)B * b, st));
+    dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
+    if (b == 32) coldot_kernel<1><<<grid, 256, 0, st>>>(N, A, Bm, out);
+    else if (b == 64) coldot_kernel<2><<<grid, 256, 0, st>>>(N, A, Bm, out);
+    else return SCB_ERR_UNSUPPORTED;
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, double* W, const double* alpha,
+                 const double* beta_prev, const double* nrm2, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
+    if (b == 32) lanczos_axpy_kernel<1><<<grid, 256, 0, st>>>(N, mode, V, Vprev, W, alpha, beta_prev, nrm2);
+    else if (b == 64) lanczos_axpy_kernel<2><<<grid, 256, 0, st>>>(N, mode, V, Vprev, W, alpha, beta_prev, nrm2);
+    else return SCB_ERR_UNSUPPORTED;
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+int lanczos_bound(int B, int b, int k, const double* alpha, const double* beta2, EigState* state, cudaStream_t st) {
+    lanczos_bound_kernel<<<B, 128, 0, st>>>(B, b, k, alpha, beta2, state);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
 
 // ---------------------------------------------------------------------------
 // analytic null space: translations + rotations (D=3) or the constant vector

@@ -8,6 +8,7 @@ struct EigState {
     double ub;       // upper bound of the spectrum
     double lo;       // lower edge of the damped interval (largest Ritz value of the block)
     double a0;       // lowest Ritz value (scaling point of the filter)
+    double ub_safe;  // guaranteed bound (Gershgorin); ub may be a tighter Lanczos estimate
     int32_t iters;
     int32_t converged;
 };
@@ -16,11 +17,12 @@ int spmm_cheb(int D, int B, int n, const int64_t* rowptr, const int32_t* col, co
               const double* diag, const double* X, const double* W, double* Y, int b, const double* coef,
               int coef_stride, const int32_t* done, cudaStream_t st);
 size_t paired_capacity(int B, int n, int64_t P);
+size_t paired_entry_bytes(int D);
 int build_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
-                 const double* diag, int32_t* pcount, int32_t* pcol, double* pblk, cudaStream_t st);
-int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const int32_t* pcol,
-                const double* pblk, const double* X, const double* W, double* Y, int b, const double* coef,
-                int coef_stride, const int32_t* done, cudaStream_t st);
+                 const double* diag, int32_t* pcount, void* pent, cudaStream_t st);
+int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const void* pent,
+                const double* X, const double* W, double* Y, int b, const double* coef, int coef_stride,
+                const int32_t* done, cudaStream_t st);
 int gram(int B, int64_t N, int b, const double* A, const double* Bm, double* G, const int32_t* done, cudaStream_t st);
 int small_rr(int B, int b, const double* S, const double* T, double* theta, double* C, const int32_t* done,
              int mode, cudaStream_t st, int nact = 0);
@@ -36,6 +38,10 @@ int state_update(int B, int b, int k, double tol, const double* theta, const dou
                  int32_t* done, int32_t* n_active, double* resid, cudaStream_t s);
 int cheb_coef(int B, int degree, const EigState* st, const int32_t* done, double* coef, cudaStream_t s);
 int rand_init(int64_t total, uint64_t seed, double* X, cudaStream_t s);
+int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st);
+int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, double* W, const double* alpha,
+                 const double* beta_prev, const double* nrm2, cudaStream_t st);
+int lanczos_bound(int B, int b, int k, const double* alpha, const double* beta2, EigState* state, cudaStream_t st);
 int gather_results(int B, int b, const double* theta, const EigState* st, double* eigval, int32_t* iters,
                    cudaStream_t s);
 
