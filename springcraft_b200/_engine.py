@@ -220,7 +220,7 @@ class DeviceModel:
                                                _lib.ptr(Z), _lib.stream_ptr()))
         return Z
 
-    def eig_lowest(self, k, deflate=True, tol=3e-9, max_outer=300, degree=20, seed=0x5CB200, b=None):
+    def eig_lowest(self, k, deflate=True, tol=3e-9, max_outer=300, degree=24, seed=0x5CB200, b=None):
         """The k lowest modes of the (optionally rigid-body deflated) operator.
 
         Returns (eigval[B][b], X[B][N][b], resid[B][b], iters[B]) device tensors;

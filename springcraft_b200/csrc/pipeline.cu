@@ -2,6 +2,8 @@
 // The host-buffer variant is the drop-in for the reference-side loop
 //   for c in conformations: ANM(c, ff).eigen(); mean_square_fluctuation(...)
 // (anm.py:62-148 + nma.py:29-184), with H2D/D2H inside.
+#include <stdlib.h>
+
 #include "subspace.cuh"
 
 namespace scb {
@@ -104,7 +106,9 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
     SCB_TRY(scb_contacts_fill(xyz, B, n, ff->cutoff_sq, patch, 0, rowptr, col, st));
     SCB_TRY(scb_assemble(D, xyz, B, n, ff, rowptr, col, masses, offdiag, diag, gersh, flag, st));
     SCB_TRY(scb_rigid_basis(D, xyz, B, n, masses, Z, st));
-    int status = scb_eig_lowest(D, B, n, P, rowptr, col, offdiag, diag, gersh, Z, nz, k, b, tol, 200, 20,
+    int degree = 24;
+    if (const char* env = getenv("SCB_DEGREE")) degree = atoi(env) >= 2 ? atoi(env) : degree;
+    int status = scb_eig_lowest(D, B, n, P, rowptr, col, offdiag, diag, gersh, Z, nz, k, b, tol, 200, degree,
                                 0x5cb200ull, theta, X, resid, it, ws, ws_bytes, st);
     if (status != SCB_OK && status != SCB_ERR_NOT_CONVERGED) return status;
     slice_eigval_kernel<<<(unsigned)ceil_div((int64_t)B * k, 256), 256, 0, st>>>(B, b, 0, k, theta, eigval);

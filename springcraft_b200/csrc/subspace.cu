@@ -3,6 +3,8 @@
 // Jacobi in shared memory), basis rotation, deflation of the analytic null
 // space, residual norms and the per-structure solver state.  "Only the small
 // Rayleigh-Ritz solve is done densely" (BASELINE.json north_star).
+#include <stdlib.h>
+
 #include "subspace.cuh"
 #include "jacobi.cuh"
 
@@ -623,7 +625,7 @@ lanczos_axpy_kernel(int64_t N, int mode, double* __restrict__ V, double* __restr
 // largest eigenvalue of each column's k x k Lanczos tridiagonal (bisection on the
 // Sturm count), max over columns -> tightened upper bound in the solver state
 __global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restrict__ alpha,
-                                     const double* __restrict__ beta2, EigState* st) {
+                                     const double* __restrict__ beta2, EigState* st, double ub_factor) {
     // alpha[j][s][c], beta2[j][s][c] = beta_j^2 (coupling between steps j and j+1)
     const int s = blockIdx.x;
     const int c = threadIdx.x;
@@ -660,7 +662,7 @@ __global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restri
         double m = 0.0;
         for (int q = 0; q < b; ++q) m = fmax(m, best[q]);
         EigState e = st[s];
-        const double est = 1.05 * m;
+        const double est = ub_factor * m;
         if (est > 0.0 && est < e.ub) e.ub = est;
         st[s] = e;
     }
@@ -687,7 +689,9 @@ int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, do
 }
 
 int lanczos_bound(int B, int b, int k, const double* alpha, const double* beta2, EigState* state, cudaStream_t st) {
-    lanczos_bound_kernel<<<B, 128, 0, st>>>(B, b, k, alpha, beta2, state);
+    double ub_factor = 1.03;
+    if (const char* env = getenv("SCB_UBFACTOR")) ub_factor = atof(env) > 1.0 ? atof(env) : ub_factor;
+    lanczos_bound_kernel<<<B, 128, 0, st>>>(B, b, k, alpha, beta2, state, ub_factor);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }

@@ -307,6 +307,30 @@ def test_c3_ensemble_api():
         assert res.n_pairs == sum(int(ref[f"c{c}/{key}/n_pairs"]) for c in members)
 
 
+def test_chain1500_lowest_modes_vs_oracle():
+    """Sparse lowest-k path on a mid-size system (cell-list contacts are used from n=2048 on, so
+    both a 1,500- and a 2,500-residue chain are checked) against the oracle's dense eigh."""
+    for n, use_eigh in ((1500, True), (2500, False)):
+        coord = orc.synthetic_chain(n, seed=5)
+        anm = sc.ANM(coord, sc.InvariantForceField(13.0))
+        lam, modes = anm.eigen(k=26)
+        Ho, pairs_o = orc.compute_hessian(coord, orc.FFSpec("invariant", 13.0))
+        assert anm._model_device().P == len(pairs_o)
+        scale = np.abs(Ho).sum(1).max()
+        # residuals against the ORACLE's matrix: || H u - lam u || small, modes orthonormal
+        R = Ho @ modes[6:].T - modes[6:].T * lam[6:]
+        assert np.abs(R).max() <= 1e-9 * scale
+        assert np.allclose(modes @ modes.T, np.eye(26), atol=1e-10)
+        assert np.abs(Ho @ modes[:6].T).max() <= 1e-9 * scale        # analytic rigid-body modes
+        if use_eigh:
+            want, vec = np.linalg.eigh(Ho)
+            assert np.allclose(lam[6:26], want[6:26], rtol=EIG_RTOL, atol=0)
+            assert subspace_sin(modes[6:26], vec.T[6:26]) < ANGLE_TOL
+            msf = anm.mean_square_fluctuation(mode_subset=np.arange(6, 26))
+            want_msf = orc.mean_square_fluctuation(want, vec.T, 3, mode_subset=np.arange(6, 26))
+            assert np.allclose(msf, want_msf, rtol=PROD_RTOL, atol=0)
+
+
 @pytest.mark.parametrize("key", ["invariant13", "e_anm"])
 def test_7cal_lowest_modes(structures, key):
     """1,776-residue tetramer (test_anm.py:60-84 structure), lowest modes."""
