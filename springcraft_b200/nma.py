@@ -63,7 +63,8 @@ def _low_spectrum(enm, k_total):
 def eigen(enm, *, k=None):
     """Eigenvalues (ascending) and eigenvectors as rows (nma.py:29-63)."""
     _kind(enm)
-    if k is None or not enm._has_model():
+    if k is None or not enm._has_model() or int(k) > LOWEST_K_MAX:
+        # every mode (or more than the lowest-k solver's block holds): dense block-Jacobi path
         lam, modes = _full_spectrum(enm)
         if k is not None:
             lam, modes = lam[:k], modes[:k]

@@ -7,7 +7,7 @@ torch.distributed for the plumbing.
   of the output; each rank calls the C ABI with its [row0, row1) range.
 """
 
-__all__ = ["shard_range", "row_slab", "gather_results", "world"]
+__all__ = ["shard_range", "row_slab", "gather_results", "world", "dcc_row_partitioned"]
 
 
 def world():
@@ -56,3 +56,20 @@ def gather_results(local, total, dim=0):
     parts = [torch.empty_like(padded) for _ in range(ws)]
     dist.all_gather(parts, padded)
     return torch.cat([p.narrow(dim, 0, b - a) for p, (a, b) in zip(parts, sizes)], dim=dim)
+
+
+def dcc_row_partitioned(D, lam, modes, norm=True, scale=1.0, gather=False):
+    """every rank computes the rows [row0,row1) of the DCC /
+    covariance contraction sum_k U_k U_k^T / lam_k with the DMMA kernel
+    (`scb_dcc` takes the row range); the (lam, modes) operands are replicated.
+    No exchange is needed inside the contraction (the normalisation uses the
+    locally recomputed diagonal).  Returns (row0, row1, slab) or, with
+    gather=True, the full matrix on every rank."""
+    from . import _engine
+    rank, ws = world()
+    n = int(modes.shape[1]) // D
+    row0, row1 = row_slab(n, rank, ws)
+    slab = _engine.modes_dcc(D, lam, modes, norm=norm, scale=scale, rows=(row0, row1))
+    if not gather:
+        return row0, row1, slab
+    return gather_results(slab, n, dim=0)

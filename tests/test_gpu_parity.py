@@ -345,6 +345,27 @@ def test_7cal_lowest_modes(structures, key):
     assert np.allclose(msf, ref[f"{key}/msf_6_26"], rtol=PROD_RTOL, atol=0)
 
 
+def test_c4_cloud400_allpairs_100_modes():
+    """Config C4 scaled down: ParameterFree all-pairs Hessian, lowest 100 non-trivial modes + MSF."""
+    ref = golden("ref_c4_cloud400.npz")
+    anm = sc.ANM(ref["coord"], sc.ParameterFreeForceField())
+    assert rel_err(np.diagonal(anm.hessian), ref["hessian_diag"]) <= HESS_RTOL
+    lam, modes = anm.eigen(k=106)
+    assert np.allclose(lam[6:106], ref["eigval"][6:106], rtol=EIG_RTOL, atol=0)
+    assert subspace_sin(modes[6:106], ref["modes_6_106"]) < ANGLE_TOL
+    msf = anm.mean_square_fluctuation(mode_subset=np.arange(6, 106))
+    assert np.allclose(msf, ref["msf_6_106"], rtol=PROD_RTOL, atol=0)
+    # the dense row-slab assembly (C4 partitioning, scb_assemble_dense_allpairs) agrees with the BSR path
+    import ctypes, torch
+    from springcraft_b200 import _lib
+    model = anm._model_device()
+    n = model.n
+    slab = torch.empty((3 * (300 - 100), 3 * n), dtype=torch.float64, device="cuda")
+    _lib.check(model.handle.scb_assemble_dense_allpairs(3, _lib.ptr(model.xyz), n, ctypes.byref(model.desc), None,
+                                                        100, 300, _lib.ptr(slab), _lib.stream_ptr()))
+    assert rel_err(slab.cpu().numpy(), anm.hessian[300:900]) <= HESS_RTOL
+
+
 # --------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("key", ["invariant13", "hinsen", "e_anm", "sd_enm", "pfree"])
 def test_1l2y_nma_products(structures, key):
