@@ -287,7 +287,8 @@ def run_gpu(args):
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "spmm_paired_kernel<3> (row-paired BSR 6x3 x 32-column block)", "achieved": achieved,
                 "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": None, "ms_per_launch": spmm_ms, "bytes_per_launch": alg_bytes,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1h)
+                "traffic": 7.415e9, "ms_per_launch": spmm_ms, "bytes_per_launch": alg_bytes,
                 "fp64_gflops": alg_flops / (spmm_ms * 1e-3) / 1e9}
 
     # ---- CPU baseline beside it (bounded sample, rank 0 only)

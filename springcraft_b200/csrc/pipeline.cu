@@ -17,6 +17,20 @@ __global__ void aos_to_soa_kernel(const double* __restrict__ aos, int64_t total_
     for (int a = 0; a < 3; ++a) soa[(s * 3 + a) * n + i] = aos[q * 3 + a];
 }
 
+// small systems: modes_out[s][q][r] = modes_full[s][k0+q][r], eigval_out[s][q] = lam_full[s][k0+q]
+__global__ void slice_full_kernel(int B, int N, int k0, int k, const double* __restrict__ lam_full,
+                                  const double* __restrict__ modes_full, double* __restrict__ eigval,
+                                  double* __restrict__ modes) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)B * k * N;
+    if (q >= total) return;
+    const int64_t s = q / ((int64_t)k * N);
+    const int64_t rem = q % ((int64_t)k * N);
+    const int m = (int)(rem / N), r = (int)(rem % N);
+    modes[q] = modes_full[(s * N + k0 + m) * N + r];
+    if (r == 0) eigval[s * k + m] = lam_full[s * N + k0 + m];
+}
+
 // eigval_out[s][q] = theta[s][k0+q]
 __global__ void slice_eigval_kernel(int B, int b, int k0, int k, const double* __restrict__ theta,
                                     double* __restrict__ out) {
@@ -76,6 +90,8 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
     const int nz = (D == 3) ? 6 : 1;
     const int b = (k + 8 <= 32) ? 32 : 64;
     if (k + 4 > b) return SCB_ERR_UNSUPPORTED;
+    const bool small = (int64_t)D * n < b + nz + 8;  // block wider than the space: dense full-spectrum path
+    if (small && nz + k > D * n) return SCB_ERR_INVALID;
     const int64_t nrows = (int64_t)B * n;
     const int64_t N = (int64_t)D * n;
     Scratch sc(st);
@@ -105,6 +121,30 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
     SCB_TRY(sc.alloc((char**)&ws, ws_bytes));
     SCB_TRY(scb_contacts_fill(xyz, B, n, ff->cutoff_sq, patch, 0, rowptr, col, st));
     SCB_TRY(scb_assemble(D, xyz, B, n, ff, rowptr, col, masses, offdiag, diag, gersh, flag, st));
+    if (small) {
+        // tiny structures (e.g. 20-residue Trp-cage): densify and run the shared-memory / block Jacobi solver
+        const int64_t NN = N * N;
+        double *dense, *lam_full, *modes_full, *modes_k; void* fws;
+        SCB_TRY(sc.alloc(&dense, (size_t)B * NN));
+        SCB_TRY(sc.alloc(&lam_full, (size_t)B * N));
+        SCB_TRY(sc.alloc(&modes_full, (size_t)B * NN));
+        SCB_TRY(sc.alloc(&modes_k, (size_t)B * k * N));
+        const size_t fbytes = scb_eig_full_workspace_bytes(B, (int)N);
+        SCB_TRY(sc.alloc((char**)&fws, fbytes));
+        SCB_TRY(scb_densify(D, B, n, rowptr, col, offdiag, diag, dense, st));
+        SCB_TRY(scb_eig_full(B, (int)N, dense, lam_full, modes_full, fws, fbytes, st));
+        const int64_t total = (int64_t)B * k * N;
+        slice_full_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(B, (int)N, nz, k, lam_full, modes_full,
+                                                                         eigval, modes_k);
+        SCB_LAUNCH_CHECK();
+        SCB_TRY(scb_msf(D, B, n, k, eigval, modes_k, 1.0, msf, st));
+        if (modes) SCB_CUDA(cudaMemcpyAsync(modes, modes_k, sizeof(double) * (size_t)total, cudaMemcpyDeviceToDevice, st));
+        if (iters) SCB_CUDA(cudaMemsetAsync(iters, 0, sizeof(int32_t) * B, st));
+        int32_t hflag = 0;
+        SCB_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        return hflag != 0 ? hflag : SCB_OK;
+    }
     SCB_TRY(scb_rigid_basis(D, xyz, B, n, masses, Z, st));
     int degree = 24;
     if (const char* env = getenv("SCB_DEGREE")) degree = atoi(env) >= 2 ? atoi(env) : degree;

@@ -23,7 +23,7 @@
 
 namespace scb {
 
-constexpr int kPairWarps = 16;     // warps per CTA (128 registers per thread available)
+constexpr int kPairWarps = 16;     // warps per CTA (128 registers per thread; 24 warps x 80 registers spills)
 constexpr int kPairChunk = 16;     // merged contacts staged per warp and round (4 per slot)
 
 template <int D>

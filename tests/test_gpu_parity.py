@@ -331,6 +331,30 @@ def test_chain1500_lowest_modes_vs_oracle():
             assert np.allclose(msf, want_msf, rtol=PROD_RTOL, atol=0)
 
 
+def test_ensemble_gnm_and_tiny_systems(structures):
+    """Batched path for GNM (D=1) and for structures smaller than the solver block (dense fallback)."""
+    ref = golden("ref_c3_chain300.npz")
+    coords = np.stack([orc.perturbed_conformation(ref["base"], c) for c in (0, 1, 2)])
+    res = sc.enm_ensemble(coords, sc.InvariantForceField(10.0), k=20, kind="gnm", return_modes=True)
+    for q in range(3):
+        K, _ = orc.compute_kirchhoff(coords[q], orc.FFSpec("invariant", 10.0))
+        lam, vec = np.linalg.eigh(K)
+        assert np.allclose(res.eigenvalues[q], lam[1:21], rtol=EIG_RTOL, atol=0)
+        assert subspace_sin(res.modes[q], vec.T[1:21]) < ANGLE_TOL
+        want = orc.mean_square_fluctuation(lam, vec.T, 1, mode_subset=np.arange(1, 21))
+        assert np.allclose(res.msf[q], want, rtol=PROD_RTOL, atol=0)
+    # 20-residue Trp-cage: N = 60 < block width -> shared-memory Jacobi path, same API
+    g = golden("ref_1l2y.npz")
+    c = structures["1l2y_coord"].astype(np.float64)
+    rng = np.random.default_rng(3)
+    tiny = np.stack([c, c + rng.normal(0, 0.05, c.shape)])
+    res = sc.enm_ensemble(tiny, sc.InvariantForceField(13.0), k=20, return_modes=True)
+    assert np.allclose(res.eigenvalues[0], g["invariant13/anm_eigval"][6:26], rtol=EIG_RTOL)
+    assert np.allclose(res.msf[0], g["invariant13/anm_msf_sub"], rtol=PROD_RTOL)
+    H1, _ = orc.compute_hessian(tiny[1], orc.FFSpec("invariant", 13.0))
+    assert np.allclose(res.eigenvalues[1], np.linalg.eigvalsh(H1)[6:26], rtol=EIG_RTOL)
+
+
 @pytest.mark.parametrize("key", ["invariant13", "e_anm"])
 def test_7cal_lowest_modes(structures, key):
     """1,776-residue tetramer (test_anm.py:60-84 structure), lowest modes."""
