@@ -20,10 +20,10 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
 // initialised by the caller).  Called by all 256 threads of the CTA.
 template <int LD>
 __device__ void jacobi_eigen_smem(double* A, double* V, int m, double* cs, double* sn, int* pp, int* qq,
-                                  double* red, int vrows) {
+                                  double* red, int vrows, int max_sweeps = 30) {
     const int half = m / 2;       // m is even
     const int tid = threadIdx.x;
-    for (int sweep = 0; sweep < 30; ++sweep) {
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         double off = 0.0, dg = 0.0;
         for (int q = tid; q < m * m; q += 256) {
             const int i = q / m, j = q % m;
