@@ -184,6 +184,35 @@ int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t *rowptr, const 
                    const double *Z, int nz, int k, int b, double tol, int max_outer,
                    int degree, uint64_t seed, double *eigval, double *X, double *resid,
                    int32_t *iters, void *workspace, size_t workspace_bytes, void *stream);
+/* ---- dense row-slab operator + solver building blocks (all-pairs force fields).
+ * The Python host code drives the same Chebyshev-filtered subspace iteration with these, putting a
+ * torch.distributed all-gather of the row slabs of Y between scb_dense_slab_apply calls. ---- */
+/* Y[rows][b] = H[rows,:] X                      (fused == 0)
+ *            = alpha (H[rows,:] X - c X[rows]) - beta W[rows]   (fused != 0);  rows = [row0,row1) of
+ * the N x N matrix, slab = those rows (row-major, N columns); X, W are full [N][b]; b % 64 == 0. */
+int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const double *slab,
+                         const double *X, const double *W, double *Y, int b, int fused,
+                         double alpha, double cshift, double beta, void *stream);
+/* out[0] = max row sum of |entries| over the slab rows (Gershgorin bound of the local rows) */
+int scb_dense_gershgorin(int64_t N, int64_t rows, const double *slab, double *out, void *stream);
+/* G[B][b][b] = A^T Bm  for block vectors [B][N][b]  (b = 32, 64, 128) */
+int scb_gram(int B, int64_t N, int b, const double *A, const double *Bm, double *G, void *stream);
+/* S = L L^T  ->  C = L^-T  (X C is orthonormal);  b <= 160 */
+int scb_chol_orth(int B, int b, const double *S, double *C, void *stream);
+/* Xout = Xin C (and Yout = Yin C when Yin != NULL); in place allowed */
+int scb_rotate(int B, int64_t N, int b, const double *C, const double *Xin, double *Xout,
+               const double *Yin, double *Yout, void *stream);
+/* X <- X - Z (Z^T X);  scratch >= B*8*b doubles */
+int scb_deflate(int B, int64_t N, int b, int nz, const double *Z, double *X, double *scratch,
+                void *stream);
+/* rn2[B][b] = squared column norms of HX - X diag(theta) */
+int scb_residual_norms(int B, int64_t N, int b, const double *X, const double *HX,
+                       const double *theta, double *rn2, void *stream);
+/* out = in^T for a b x b matrix (mode rows -> rotation columns) */
+int scb_transpose_small(int b, const double *in, double *out, void *stream);
+/* deterministic pseudo-random block in (-1, 1) */
+int scb_rand_block(int64_t total, uint64_t seed, double *X, void *stream);
+
 /* full symmetric eigendecomposition of dense A[B][N][N] (lower triangle is
  * referenced, like LAPACK dsyevd behind np.linalg.eigh): eigval[B][N] ascending,
  * modes[B][N][N] with ROW k = mode k (nma.py:63).  A is destroyed. */

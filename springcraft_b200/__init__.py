@@ -6,6 +6,7 @@ __reference_version__ = "0.3.0"
 
 from . import nma  # noqa: F401
 from .anm import *  # noqa: F401,F403
+from .dense_solver import *  # noqa: F401,F403
 from .ensemble import *  # noqa: F401,F403
 from .forcefield import *  # noqa: F401,F403
 from .gnm import *  # noqa: F401,F403

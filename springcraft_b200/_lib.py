@@ -85,6 +85,15 @@ SIGNATURES = {
     "scb_eig_lowest_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I64]),
     "scb_eig_lowest": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _I, _I, _I, _D, _I, _I, _U64,
                             _P, _P, _P, _P, _P, _SZ, _P]),
+    "scb_dense_slab_apply": (_I, [_I64, _I64, _I64, _P, _P, _P, _P, _I, _I, _D, _D, _D, _P]),
+    "scb_dense_gershgorin": (_I, [_I64, _I64, _P, _P, _P]),
+    "scb_gram": (_I, [_I, _I64, _I, _P, _P, _P, _P]),
+    "scb_chol_orth": (_I, [_I, _I, _P, _P, _P]),
+    "scb_rotate": (_I, [_I, _I64, _I, _P, _P, _P, _P, _P, _P]),
+    "scb_deflate": (_I, [_I, _I64, _I, _I, _P, _P, _P, _P]),
+    "scb_residual_norms": (_I, [_I, _I64, _I, _P, _P, _P, _P, _P]),
+    "scb_transpose_small": (_I, [_I, _P, _P, _P]),
+    "scb_rand_block": (_I, [_I64, _U64, _P, _P]),
     "scb_eig_full_workspace_bytes": (_SZ, [_I, _I]),
     "scb_eig_full": (_I, [_I, _I, _P, _P, _P, _P, _SZ, _P]),
     "scb_msf": (_I, [_I, _I, _I, _I, _P, _P, _D, _P, _P]),

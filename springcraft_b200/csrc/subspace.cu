@@ -70,6 +70,7 @@ int gram(int B, int64_t N, int b, const double* A, const double* Bm, double* G, 
     dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
     if (b == 32) gram_kernel<32><<<grid, 256, 0, st>>>(N, A, Bm, G, done);
     else if (b == 64) gram_kernel<64><<<grid, 256, 0, st>>>(N, A, Bm, G, done);
+    else if (b == 128) gram_kernel<128><<<grid, 256, 0, st>>>(N, A, Bm, G, done);
     else return SCB_ERR_UNSUPPORTED;
     SCB_LAUNCH_CHECK();
     return SCB_OK;
@@ -269,6 +270,13 @@ int rotate(int B, int64_t N, int b, const double* C, const double* Xin, double* 
         rotate_kernel<32><<<grid, 256, smem, st>>>(N, C, Xin, Xout, Yin, Yout, done);
     } else if (b == 64) {
         rotate_kernel<64><<<grid, 256, smem, st>>>(N, C, Xin, Xout, Yin, Yout, done);
+    } else if (b == 128) {
+        static bool configured = false;
+        if (!configured) {
+            SCB_CUDA(cudaFuncSetAttribute(rotate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        rotate_kernel<128><<<grid, 256, smem, st>>>(N, C, Xin, Xout, Yin, Yout, done);
     } else {
         return SCB_ERR_UNSUPPORTED;
     }
@@ -286,7 +294,6 @@ __global__ void __launch_bounds__(256)
 ztx_kernel(int64_t N, int nz, const double* __restrict__ Z, const double* __restrict__ X, double* __restrict__ P,
            const int32_t* __restrict__ done) {
     constexpr int BW = 32 * CC;
-    __shared__ double red[8][kMaxNz][BW];
     const int s = blockIdx.y;
     if (done && done[s]) return;
     const double* Zs = Z + (int64_t)s * N * nz;
@@ -312,17 +319,12 @@ ztx_kernel(int64_t N, int nz, const double* __restrict__ Z, const double* __rest
                 for (int cc = 0; cc < CC; ++cc) acc[z][cc] = fma(zv, x[cc], acc[z][cc]);
             }
     }
+    // one atomic per warp, null vector and column (nz * BW * 8 per CTA)
 #pragma unroll
     for (int z = 0; z < kMaxNz; ++z)
+        if (z < nz)
 #pragma unroll
-        for (int cc = 0; cc < CC; ++cc) red[warp][z][lane + 32 * cc] = acc[z][cc];
-    __syncthreads();
-    for (int q = threadIdx.x; q < nz * BW; q += 256) {
-        const int z = q / BW, c = q % BW;
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += red[w][z][c];
-        atomicAdd(&P[((int64_t)s * kMaxNz + z) * BW + c], t);
-    }
+            for (int cc = 0; cc < CC; ++cc) atomicAdd(&P[((int64_t)s * kMaxNz + z) * BW + lane + 32 * cc], acc[z][cc]);
 }
 
 template <int CC>
@@ -368,6 +370,10 @@ int deflate(int B, int64_t N, int b, int nz, const double* Z, double* X, double*
     } else if (b == 64) {
         ztx_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
         subz_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
+        count_launches(1);
+    } else if (b == 128) {
+        ztx_kernel<4><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
+        subz_kernel<4><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
         count_launches(1);
     } else {
         return SCB_ERR_UNSUPPORTED;
@@ -418,6 +424,7 @@ int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, c
     dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
     if (b == 32) resid_kernel<1><<<grid, 256, 0, st>>>(N, X, HX, theta, rn2, done);
     else if (b == 64) resid_kernel<2><<<grid, 256, 0, st>>>(N, X, HX, theta, rn2, done);
+    else if (b == 128) resid_kernel<4><<<grid, 256, 0, st>>>(N, X, HX, theta, rn2, done);
     else return SCB_ERR_UNSUPPORTED;
     SCB_LAUNCH_CHECK();
     return SCB_OK;

@@ -1,0 +1,178 @@
+"""Lowest-k modes of DENSE interaction matrices (all-pairs force fields), row-partitioned over the
+GPUs of one node.
+
+Every rank owns a slab of rows of the N x N matrix, assembled locally from the replicated
+coordinates (`scb_assemble_dense_allpairs`: no exchange at assembly, diagonal blocks are local row
+sums).  The eigensolver is the same Chebyshev-filtered subspace iteration as the sparse path; per
+operator application each rank computes its rows of Y = H X on the FP64 tensor cores
+(`scb_dense_slab_apply`, Chebyshev recurrence fused) and the row slabs are all-gathered with
+torch.distributed (NCCL over NVLink).  The tall-skinny steps and the small Rayleigh-Ritz problem are
+replicated on every rank (they are tiny next to the slab read).  This module only orchestrates C-ABI
+kernels; the scalars of the filter live on the host (one device->host read per outer iteration).
+"""
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _engine, _lib
+from .parallel import gather_results, row_slab, world
+
+__all__ = ["DenseRowOperator", "eig_lowest_dense", "allpairs_lowest_modes"]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DenseRowOperator:
+    """Rows [row0, row1) (node units) of the dense interaction matrix of ONE structure."""
+
+    def __init__(self, coord, force_field, D=3, masses=None):
+        torch = _torch()
+        self.handle = _lib.require_device()
+        coord = np.asarray(coord, dtype=np.float64)
+        if coord.ndim != 2 or coord.shape[1] != 3:
+            raise ValueError(f"Expected coordinates with shape (n,3), got {coord.shape}")
+        if force_field.cutoff_distance is not None:
+            raise ValueError("the dense row-partitioned path is for force fields without a cutoff")
+        if force_field.contact_shutdown is not None or force_field.contact_pair_off is not None \
+                or force_field.contact_pair_on is not None:
+            raise NotImplementedError("contact patches are not supported on the dense all-pairs path")
+        built = force_field._descriptor(len(coord))
+        if built is None:
+            raise NotImplementedError("user-defined ForceField subclasses are not supported on the dense path")
+        self.desc, self._keep = built
+        self.D, self.n = int(D), len(coord)
+        self.N = self.D * self.n
+        self.rank, self.world = world()
+        self.row0, self.row1 = row_slab(self.n, self.rank, self.world)
+        self.xyz = torch.from_numpy(np.ascontiguousarray(coord.T)).cuda()[None].contiguous()  # SoA [1][3][n]
+        self.masses = None if masses is None else _lib.to_device(np.asarray(masses, dtype=np.float64), torch.float64)
+        rows = (self.row1 - self.row0) * self.D
+        self.slab = torch.empty((rows, self.N), dtype=torch.float64, device="cuda")
+        _lib.check(self.handle.scb_assemble_dense_allpairs(
+            self.D, _lib.ptr(self.xyz), self.n, C.byref(self.desc), _lib.ptr(self.masses), self.row0, self.row1,
+            _lib.ptr(self.slab), _lib.stream_ptr()))
+
+    # -- operator ---------------------------------------------------------------
+    def apply(self, X, W=None, coeffs=None):
+        """Y = H X (coeffs None) or alpha (H X - c X) - beta W; returns the full [N][b] block."""
+        torch = _torch()
+        b = int(X.shape[1])
+        local = torch.empty(((self.row1 - self.row0) * self.D, b), dtype=torch.float64, device="cuda")
+        alpha, cshift, beta = coeffs if coeffs is not None else (1.0, 0.0, 0.0)
+        _lib.check(self.handle.scb_dense_slab_apply(
+            self.N, self.row0 * self.D, self.row1 * self.D, _lib.ptr(self.slab), _lib.ptr(X), _lib.ptr(W),
+            _lib.ptr(local), b, int(coeffs is not None), float(alpha), float(cshift), float(beta), _lib.stream_ptr()))
+        if self.world == 1:
+            return local
+        # all-gather of the row slabs (node granularity so that ragged splits stay aligned)
+        full = gather_results(local.view(self.row1 - self.row0, self.D * b), self.n, dim=0)
+        return full.view(self.N, b)
+
+    def spectrum_bound(self):
+        """Gershgorin upper bound of the spectrum (max over ranks)."""
+        torch = _torch()
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        _lib.check(self.handle.scb_dense_gershgorin(self.N, self.slab.shape[0], _lib.ptr(self.slab), _lib.ptr(out),
+                                                    _lib.stream_ptr()))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out, op=dist.ReduceOp.MAX)
+        return float(out.item())
+
+    def rigid_basis(self):
+        torch = _torch()
+        nz = 6 if self.D == 3 else 1
+        Z = torch.empty((1, self.N, nz), dtype=torch.float64, device="cuda")
+        _lib.check(self.handle.scb_rigid_basis(self.D, _lib.ptr(self.xyz), 1, self.n, _lib.ptr(self.masses),
+                                               _lib.ptr(Z), _lib.stream_ptr()))
+        return Z[0]
+
+
+def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200):
+    """The k lowest modes of the operator deflated by Z ([N][nz], orthonormal): returns
+    (theta[b], X[N][b], resid[b], outer_iterations).  Columns 0..k-1 are converged to
+    ``||H x - theta x|| <= tol * theta_k``."""
+    torch = _torch()
+    h = op.handle
+    st = _lib.stream_ptr
+    N = op.N
+    if b is None:
+        b = 64 if k + 8 <= 64 else 128
+    if k > b or b not in (64, 128):
+        raise NotImplementedError(f"k={k} needs a block wider than 128 columns")
+    nz = 0 if Z is None else int(Z.shape[1])
+    if N < b + nz:
+        raise NotImplementedError("system smaller than the solver block: use the full-spectrum solver")
+    f64 = dict(dtype=torch.float64, device="cuda")
+    A = torch.empty((N, b), **f64)
+    scratch = torch.zeros(8 * b, **f64)
+    G = torch.empty((b, b), **f64)
+    Cm = torch.empty((b, b), **f64)
+    rn2 = torch.empty(b, **f64)
+    _lib.check(h.scb_rand_block(N * b, seed, _lib.ptr(A), st()))
+    ub = op.spectrum_bound() * (1.0 + 1e-10)
+    theta = None
+    lo = a0 = 0.0
+    cur = A
+
+    def orthonormalise(src, dst, also=None):
+        _lib.check(h.scb_gram(1, N, b, _lib.ptr(src), _lib.ptr(src), _lib.ptr(G), st()))
+        _lib.check(h.scb_chol_orth(1, b, _lib.ptr(G), _lib.ptr(Cm), st()))
+        _lib.check(h.scb_rotate(1, N, b, _lib.ptr(Cm), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(also), _lib.ptr(also), st()))
+
+    for outer in range(max_outer + 1):
+        if outer > 0:
+            half, c = 0.5 * (ub - lo), 0.5 * (ub + lo)
+            sigma1 = half / (a0 - c)
+            sigma = sigma1
+            prev = A
+            curb = op.apply(prev, None, (sigma1 / half, c, 0.0))
+            for _ in range(1, degree):
+                sigma2 = 1.0 / (2.0 / sigma1 - sigma)
+                nxt = op.apply(curb, prev, (2.0 * sigma2 / half, c, sigma * sigma2))
+                prev, curb, sigma = curb, nxt, sigma2
+            cur = curb
+        if nz:
+            _lib.check(h.scb_deflate(1, N, b, nz, _lib.ptr(Z), _lib.ptr(cur), _lib.ptr(scratch), st()))
+        orthonormalise(cur, A)
+        HX = op.apply(A)
+        orthonormalise(A, A, also=HX)          # second pass (CholQR2); H (A C) = (H A) C
+        _lib.check(h.scb_gram(1, N, b, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(G), st()))
+        lam, modes = _engine.eig_full_dense(G.clone())
+        theta = lam[0].contiguous()
+        _lib.check(h.scb_transpose_small(b, _lib.ptr(modes[0]), _lib.ptr(Cm), st()))
+        _lib.check(h.scb_rotate(1, N, b, _lib.ptr(Cm), _lib.ptr(A), _lib.ptr(A), _lib.ptr(HX), _lib.ptr(HX), st()))
+        _lib.check(h.scb_residual_norms(1, N, b, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(theta), _lib.ptr(rn2), st()))
+        th = theta.cpu().numpy()
+        res = np.sqrt(np.maximum(rn2.cpu().numpy(), 0.0))
+        a0 = float(th[0])
+        lo = min(float(th[b - 1]), 0.98 * ub)
+        if not lo > a0:
+            lo = a0 + 0.5 * (ub - a0)
+        if res[:k].max() <= tol * max(abs(th[k - 1]), 1e-300):
+            return theta, A, torch.from_numpy(res).cuda(), outer
+    raise RuntimeError(_lib.lib().scb_status_string(_lib.SCB_ERR_NOT_CONVERGED).decode())
+
+
+def allpairs_lowest_modes(coord, force_field, k, kind="anm", masses=None, tol=3e-9):
+    """``eigen(k=...)`` for all-pairs force fields on the dense row-partitioned path: the k lowest
+    modes INCLUDING the trivial ones (analytic rigid-body basis, eigenvalue 0), rows = modes.
+    Call it from every rank of the process group; the result is replicated."""
+    torch = _torch()
+    D = 3 if kind == "anm" else 1
+    ntriv = 6 if D == 3 else 1
+    op = DenseRowOperator(coord, force_field, D, masses)
+    Z = op.rigid_basis()
+    kk = max(k - ntriv, 1)
+    theta, X, _, iters = eig_lowest_dense(op, kk, Z=Z, tol=tol)
+    lam = torch.cat([torch.zeros(ntriv, dtype=torch.float64, device="cuda"), theta[:kk]])
+    modes = torch.cat([Z.T.contiguous(), X[:, :kk].T.contiguous()])
+    return lam[:k].cpu().numpy(), modes[:k].cpu().numpy(), iters
+
+
+del math

@@ -390,6 +390,24 @@ def test_c4_cloud400_allpairs_100_modes():
     assert rel_err(slab.cpu().numpy(), anm.hessian[300:900]) <= HESS_RTOL
 
 
+@pytest.mark.parametrize("k", [56, 106])
+def test_c4_dense_row_operator(k):
+    """Dense slab operator + Python-driven subspace iteration (the multi-GPU C4 path, here on one rank):
+    block width 64 (k=56) and 128 (k=106)."""
+    import torch
+    from springcraft_b200.dense_solver import DenseRowOperator
+    ref = golden("ref_c4_cloud400.npz")
+    op = DenseRowOperator(ref["coord"], sc.ParameterFreeForceField(), 3)
+    H = sc.ANM(ref["coord"], sc.ParameterFreeForceField()).hessian
+    assert rel_err(op.slab.cpu().numpy(), H) <= HESS_RTOL
+    X = torch.from_numpy(np.random.default_rng(0).normal(size=(1200, 64))).cuda()
+    assert rel_err(op.apply(X).cpu().numpy(), H @ X.cpu().numpy()) <= 1e-13
+    lam, modes, iters = sc.allpairs_lowest_modes(ref["coord"], sc.ParameterFreeForceField(), k)
+    assert np.allclose(lam[6:k], ref["eigval"][6:k], rtol=EIG_RTOL, atol=0)
+    assert subspace_sin(modes[6:k], ref["modes_6_106"][: k - 6]) < ANGLE_TOL
+    assert np.abs(H @ modes[:6].T).max() <= 1e-10 * np.abs(H).max()
+
+
 # --------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("key", ["invariant13", "hinsen", "e_anm", "sd_enm", "pfree"])
 def test_1l2y_nma_products(structures, key):

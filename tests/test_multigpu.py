@@ -38,6 +38,14 @@ res = sc.enm_ensemble(confs[a:b], sc.InvariantForceField(13.0), k=20)
 ev = parallel.gather_results(torch.from_numpy(res.eigenvalues).cuda(), B).cpu().numpy()
 ref = sc.enm_ensemble(confs, sc.InvariantForceField(13.0), k=20).eigenvalues
 assert np.allclose(ev, ref, rtol=1e-9)
+# C4: dense all-pairs Hessian, row slabs + all-gather of the block per operator application
+from tests.conftest import golden
+g = golden("ref_c4_cloud400.npz")
+lam4, modes4, it4 = sc.allpairs_lowest_modes(g["coord"], sc.ParameterFreeForceField(), 56)
+assert np.allclose(lam4[6:56], g["eigval"][6:56], rtol=1e-8, atol=0), "C4 eigenvalues"
+A4 = g["modes_6_106"][:50]; Q, _ = np.linalg.qr(modes4[6:56].T)
+Qa, _ = np.linalg.qr(A4.T)
+assert np.linalg.norm(Q - Qa @ (Qa.T @ Q), 2) < 1e-6, "C4 subspace"
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
