@@ -11,6 +11,8 @@
 //   5. RR       T = X^T HX, S2 = X^T X -> Jacobi -> theta, C ; X <- X C, HX <- HX C
 //   6. residuals ||HX - theta X||, convergence flags, new filter bounds
 // The host polls one int32 (number of active structures) per outer iteration.
+#include <stdlib.h>
+
 #include "subspace.cuh"
 
 namespace scb {
@@ -25,6 +27,9 @@ struct EigWork {
     int32_t *done, *n_active;
     int32_t* pcount;          // row-paired operator (spmm_paired.cu)
     char* pent;
+    char* pent32;             // single-precision copy of the records (spmm_paired_f32.cu)
+    float *Xa32, *Xb32, *Xc32;
+    int32_t *skip32, *skip64; // per-structure precision of the next filter
 };
 
 static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, int degree_cap, double* X,
@@ -50,6 +55,12 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
     const size_t cap = paired_capacity(B, n, P);
     w->pcount = ar.take<int32_t>((size_t)B * ((n + 1) / 2));
     w->pent = ar.take<char>(cap * paired_entry_bytes(D));
+    w->pent32 = ar.take<char>(cap * paired_entry32_bytes(D));
+    w->Xa32 = ar.take<float>(vec);
+    w->Xb32 = ar.take<float>(vec);
+    w->Xc32 = ar.take<float>(vec);
+    w->skip32 = ar.take<int32_t>(B);
+    w->skip64 = ar.take<int32_t>(B);
     (void)nz;
     return ar.off;
 }
@@ -90,7 +101,12 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         return spmm_paired(D, B, n, rowptr, w.pcount, w.pent, Xin, Win, Yout, b, cf, stride, done, st);
     };
 
-    SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, st));
+    // early outer iterations filter in FP32 (see spmm_paired_f32.cu); SCB_FP32=0 disables it
+    int allow32 = 1;
+    if (const char* env = getenv("SCB_FP32")) allow32 = atoi(env) != 0;
+    const double switch_tol = 2e-3;
+    if (allow32) SCB_TRY(build_paired32(D, paired_capacity(B, n, P), w.pent, w.pent32, st));
+    SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, w.skip32, w.skip64, allow32, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
     SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
 
@@ -127,12 +143,28 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
             double* prev = w.A;
             double* curb = w.Bf;
             double* next = w.Cf;
-            if ((status = apply(prev, nullptr, curb, w.coef, degree * 3)) != SCB_OK) break;
+            float *p32 = w.Xa32, *c32 = w.Xb32, *n32 = w.Xc32;
+            const int64_t per_struct = N * b;
+            if (allow32) {
+                // structures in the FP32 phase: basis -> float, filter on the float buffers
+                if ((status = block_to_f32(B, per_struct, w.A, p32, w.skip32, st)) != SCB_OK) break;
+                if ((status = spmm_paired_f32(D, B, n, rowptr, w.pcount, w.pent32, p32, nullptr, c32, b, w.coef,
+                                              degree * 3, w.skip32, st)) != SCB_OK) break;
+            }
+            if ((status = spmm_paired(D, B, n, rowptr, w.pcount, w.pent, prev, nullptr, curb, b, w.coef, degree * 3,
+                                      w.skip64, st)) != SCB_OK) break;
             for (int d = 1; d < degree; ++d) {
-                if ((status = apply(curb, prev, next, w.coef + 3 * d, degree * 3)) != SCB_OK) break;
+                if (allow32) {
+                    if ((status = spmm_paired_f32(D, B, n, rowptr, w.pcount, w.pent32, c32, p32, n32, b,
+                                                  w.coef + 3 * d, degree * 3, w.skip32, st)) != SCB_OK) break;
+                    float* t32 = p32; p32 = c32; c32 = n32; n32 = t32;
+                }
+                if ((status = spmm_paired(D, B, n, rowptr, w.pcount, w.pent, curb, prev, next, b, w.coef + 3 * d,
+                                          degree * 3, w.skip64, st)) != SCB_OK) break;
                 double* t = prev; prev = curb; curb = next; next = t;
             }
             if (status != SCB_OK) break;
+            if (allow32 && (status = block_to_f64(B, per_struct, c32, curb, w.skip32, st)) != SCB_OK) break;
             cur = curb;
         }
         // ---- 2. deflate the analytic null space
@@ -151,7 +183,8 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         // ---- 6. residuals + state
         if ((status = zero_active_rn2(B, b, w.rn2, done, st)) != SCB_OK) break;
         if ((status = residual_norms(B, N, b, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
-        if ((status = state_update(B, b, k, tol, w.theta, w.rn2, w.state, w.done, w.n_active, resid, st)) != SCB_OK)
+        if ((status = state_update(B, b, k, tol, w.theta, w.rn2, w.state, w.done, w.n_active, resid, w.skip32,
+                                   w.skip64, allow32, switch_tol, st)) != SCB_OK)
             break;
         if (cudaMemcpyAsync(h_active, w.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {

@@ -434,7 +434,7 @@ int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, c
 // solver state
 // ---------------------------------------------------------------------------
 __global__ void state_init_kernel(int B, const double* __restrict__ gersh, EigState* st, int32_t* done,
-                                  int32_t* n_active) {
+                                  int32_t* n_active, int32_t* skip32, int32_t* skip64, int allow32) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) *n_active = B;
     if (s >= B) return;
@@ -447,6 +447,9 @@ __global__ void state_init_kernel(int B, const double* __restrict__ gersh, EigSt
     e.converged = 0;
     st[s] = e;
     done[s] = 0;
+    // filter precision of the next outer iteration: FP32 first (when allowed), FP64 later
+    skip32[s] = allow32 ? 0 : 1;
+    skip64[s] = allow32 ? 1 : 0;
 }
 
 __global__ void zero_active_rn2_kernel(int B, int b, double* rn2, const int32_t* done) {
@@ -458,7 +461,8 @@ __global__ void zero_active_rn2_kernel(int B, int b, double* rn2, const int32_t*
 // after a Rayleigh-Ritz step: convergence test, new filter bounds
 __global__ void state_update_kernel(int B, int b, int k, double tol, const double* __restrict__ theta,
                                     const double* __restrict__ rn2, EigState* st, int32_t* done,
-                                    int32_t* n_active, double* __restrict__ resid) {
+                                    int32_t* n_active, double* __restrict__ resid, int32_t* skip32,
+                                    int32_t* skip64, int allow32, double switch_tol) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= B || done[s]) return;
     const double* th = theta + (int64_t)s * b;
@@ -480,11 +484,17 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
     lo = fmin(lo, 0.98 * e.ub);
     if (!(lo > e.a0)) lo = e.a0 + 0.5 * (e.ub - e.a0);
     e.lo = lo;
+    bool finished = false;
     if (worst <= tol * scale) {
         e.converged = 1;
         done[s] = 1;
+        finished = true;
         atomicSub(n_active, 1);
     }
+    // the FP32 filter stalls near 2e-5 absolute residual: hand over to FP64 well before that
+    const bool use32 = allow32 && !finished && worst > switch_tol * scale;
+    skip32[s] = (finished || !use32) ? 1 : 0;
+    skip64[s] = (finished || use32) ? 1 : 0;
     st[s] = e;
 }
 
@@ -521,8 +531,9 @@ __global__ void gather_results_kernel(int B, int b, const double* __restrict__ t
     if (q < B) iters[q] = st[q].converged ? st[q].iters : -st[q].iters;
 }
 
-int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, cudaStream_t s) {
-    state_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, s>>>(B, gersh, st, done, n_active);
+int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, int32_t* skip32,
+               int32_t* skip64, int allow32, cudaStream_t s) {
+    state_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, s>>>(B, gersh, st, done, n_active, skip32, skip64, allow32);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
@@ -532,8 +543,10 @@ int zero_active_rn2(int B, int b, double* rn2, const int32_t* done, cudaStream_t
     return SCB_OK;
 }
 int state_update(int B, int b, int k, double tol, const double* theta, const double* rn2, EigState* st,
-                 int32_t* done, int32_t* n_active, double* resid, cudaStream_t s) {
-    state_update_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, b, k, tol, theta, rn2, st, done, n_active, resid);
+                 int32_t* done, int32_t* n_active, double* resid, int32_t* skip32, int32_t* skip64, int allow32,
+                 double switch_tol, cudaStream_t s) {
+    state_update_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, b, k, tol, theta, rn2, st, done, n_active, resid,
+                                                                  skip32, skip64, allow32, switch_tol);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }

@@ -23,6 +23,13 @@ int build_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* col,
 int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const void* pent,
                 const double* X, const double* W, double* Y, int b, const double* coef, int coef_stride,
                 const int32_t* done, cudaStream_t st);
+size_t paired_entry32_bytes(int D);
+int build_paired32(int D, size_t cap, const void* pent, void* pent32, cudaStream_t st);
+int block_to_f32(int B, int64_t per_struct, const double* in, float* out, const int32_t* skip, cudaStream_t st);
+int block_to_f64(int B, int64_t per_struct, const float* in, double* out, const int32_t* skip, cudaStream_t st);
+int spmm_paired_f32(int D, int B, int n, const int64_t* rowptr, const int32_t* pcount, const void* pent32,
+                    const float* X, const float* W, float* Y, int b, const double* coef, int coef_stride,
+                    const int32_t* skip, cudaStream_t st);
 int gram(int B, int64_t N, int b, const double* A, const double* Bm, double* G, const int32_t* done, cudaStream_t st);
 int small_rr(int B, int b, const double* S, const double* T, double* theta, double* C, const int32_t* done,
              int mode, cudaStream_t st, int nact = 0);
@@ -32,10 +39,12 @@ int deflate(int B, int64_t N, int b, int nz, const double* Z, double* X, double*
             cudaStream_t st);
 int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, const double* theta, double* rn2,
                    const int32_t* done, cudaStream_t st);
-int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, cudaStream_t s);
+int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, int32_t* skip32,
+               int32_t* skip64, int allow32, cudaStream_t s);
 int zero_active_rn2(int B, int b, double* rn2, const int32_t* done, cudaStream_t s);
 int state_update(int B, int b, int k, double tol, const double* theta, const double* rn2, EigState* st,
-                 int32_t* done, int32_t* n_active, double* resid, cudaStream_t s);
+                 int32_t* done, int32_t* n_active, double* resid, int32_t* skip32, int32_t* skip64, int allow32,
+                 double switch_tol, cudaStream_t s);
 int cheb_coef(int B, int degree, const EigState* st, const int32_t* done, double* coef, cudaStream_t s);
 int rand_init(int64_t total, uint64_t seed, double* X, cudaStream_t s);
 int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st);
