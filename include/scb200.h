@@ -246,6 +246,13 @@ int scb_covariance(int N, int m, const double *lam, const double *modes, int row
 int scb_linear_response(int N, int m, const double *lam, const double *modes,
                         const double *force, double *out, void *workspace,
                         size_t workspace_bytes, void *stream);
+/* perturbation response scanning matrix (nma.py:511-531): out[n][n] from the covariance cov[3n][3n];
+ * norm != 0 divides row i by out[i][i] */
+int scb_prs(int n, const double *cov, int norm, double *out, void *stream);
+/* normal-mode trajectory (nma.py:402-419): out[frames][n][3] for one mode[3n]; triangle != 0 selects
+ * the "triangle" movement, else "sine" */
+int scb_normal_mode(int n, int frames, const double *mode, double amplitude, int triangle, double *out,
+                    void *stream);
 /* modes[B][m][N] <- X[B][N][b] columns k0..k0+m-1 (transpose to the reference's
  * "eigenvectors as rows" layout) */
 int scb_export_modes(int B, int N, int b, int k0, int m, const double *X, double *modes,

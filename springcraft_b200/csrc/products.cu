@@ -256,6 +256,61 @@ gemm_nt_dmma_kernel(int Mrows, int Nc, int64_t K, int64_t ldk, int row0, const d
     }
 }
 
+// perturbation response scanning (nma.py:511-531): out[i][j] = sum_{a,b} cov[3i+a][3j+b]^2, optionally / out[i][i]
+__global__ void __launch_bounds__(256)
+prs_kernel(int n, const double* __restrict__ cov, int norm, double* __restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)n * n) return;
+    const int i = (int)(q / n), j = (int)(q % n);
+    const int64_t N = 3 * (int64_t)n;
+    auto block_sq = [&](int r, int c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const double v = cov[(3 * (int64_t)r + a) * N + 3 * (int64_t)c + b];
+                acc += v * v;
+            }
+        return acc;
+    };
+    double v = block_sq(i, j);
+    if (norm) v /= block_sq(i, i);
+    out[q] = v;
+}
+
+// normal-mode trajectory (nma.py:402-419): disp[f][i][a] = shape(f) * amplitude * u[3i+a] / max_i |u_i|
+__global__ void __launch_bounds__(256)
+normal_mode_kernel(int n, int frames, const double* __restrict__ mode, double amplitude, int triangle,
+                   double* __restrict__ out) {
+    __shared__ double red[8];
+    __shared__ double smax;
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double x = mode[3 * i], y = mode[3 * i + 1], z = mode[3 * i + 2];
+        m = fmax(m, sqrt(x * x + y * y + z * z));
+    }
+    m = warp_max(m);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t = fmax(t, red[w]);
+        smax = t;
+    }
+    __syncthreads();
+    const double scale = amplitude / smax;
+    const double kTwoPi = 6.283185307179586476925286766559;
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < (int64_t)frames * 3 * n; q += (int64_t)gridDim.x * 256) {
+        const int f = (int)(q / (3 * n));
+        const double time = (double)f / frames;
+        double shape;
+        if (triangle) shape = 2.0 * fabs(2.0 * (time - floor(time + 0.5))) - 1.0;
+        else shape = sin(time * kTwoPi);
+        out[q] = shape * (mode[q % (3 * n)] * scale);
+    }
+}
+
 static int64_t padded_k(int64_t K) { return (K + 1) & ~int64_t(1); }
 
 static int run_product(int D, int n, int m, const double* lam, const double* modes, int norm, double scale,
@@ -352,6 +407,23 @@ extern "C" int scb_linear_response(int N, int m, const double* lam, const double
     lr_project_kernel<<<m, 256, 0, st>>>(N, m, lam, modes, force, t);
     SCB_LAUNCH_CHECK();
     lr_expand_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, m, modes, t, out);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+extern "C" int scb_prs(int n, const double* cov, int norm, double* out, void* stream) {
+    if (!cov || !out || n < 1) return SCB_ERR_INVALID;
+    prs_kernel<<<(unsigned)ceil_div((int64_t)n * n, 256), 256, 0, as_stream(stream)>>>(n, cov, norm, out);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+extern "C" int scb_normal_mode(int n, int frames, const double* mode, double amplitude, int triangle, double* out,
+                               void* stream) {
+    if (!mode || !out || n < 1 || frames < 1) return SCB_ERR_INVALID;
+    const int64_t total = (int64_t)frames * 3 * n;
+    const unsigned grid = (unsigned)(ceil_div(total, 256) < 1024 ? ceil_div(total, 256) : 1024);
+    normal_mode_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, frames, mode, amplitude, triangle, out);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }

@@ -160,7 +160,7 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
                 // this slot owns contacts slot, slot+4, slot+8, slot+12 of the chunk
 #pragma unroll 2
                 for (int q = slot; q < m; q += 4) {
-                    const double* xr = Xs + (int64_t)cur[q].col * rowlen;
+                    const double* xr = Xs + cur[q].col * rowlen;  // 32-bit offset inside one structure
                     double x[D][4];
 #pragma unroll
                     for (int c = 0; c < D; ++c) {

@@ -119,7 +119,7 @@ spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* _
                 const Entry* cur = stage + buf * kPairChunk;
 #pragma unroll 2
                 for (int q = slot; q < m; q += 4) {
-                    const float* xr = Xs + (int64_t)cur[q].col * rowlen;
+                    const float* xr = Xs + cur[q].col * rowlen;  // 32-bit offset inside one structure
                     float x[D][4];
 #pragma unroll
                     for (int c = 0; c < D; ++c) {

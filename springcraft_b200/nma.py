@@ -136,22 +136,24 @@ def dcc(enm, mode_subset=None, norm=True, tem=None, tem_factors=K_B):
 
 
 def normal_mode(anm, index, amplitude, frames, movement="sine"):
-    """nma.py:363-419 (SURVEY 8f "next": elementwise on one eigenvector)."""
+    """nma.py:363-419: oscillation of one mode, shape (frames, n, 3)."""
     from .anm import ANM
     if not isinstance(anm, ANM):
         raise ValueError("Instance of ANM class expected.")
-    _, eig_vectors = eigen(anm)
-    mode_vectors = eig_vectors[index].reshape((-1, 3))
-    vector_lengths = np.sqrt(np.sum(mode_vectors ** 2, axis=-1))
-    mode_vectors = mode_vectors * (amplitude / np.max(vector_lengths))
-    time = np.linspace(0, 1, frames, endpoint=False)
-    if movement == "sine":
-        normed_disp = np.sin(time * 2 * np.pi)
-    elif movement == "triangle":
-        normed_disp = 2 * np.abs(2 * (time - np.floor(time + 0.5))) - 1
-    else:
+    if movement not in ("sine", "triangle"):
         raise ValueError(f"Movement '{movement}' is unknown")
-    return normed_disp[:, np.newaxis, np.newaxis] * mode_vectors
+    import torch
+    from . import _lib
+    if anm._has_model() and 0 <= index < LOWEST_K_MAX and anm._spectrum_cache.get("full") is None:
+        _, modes = _low_spectrum(anm, index + 1)
+    else:
+        _, modes = _full_spectrum(anm)
+    n = len(anm._coord)
+    mode = modes[index].contiguous()
+    out = torch.empty((frames, n, 3), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.require_device().scb_normal_mode(n, int(frames), _lib.ptr(mode), float(amplitude),
+                                                     int(movement == "triangle"), _lib.ptr(out), _lib.stream_ptr()))
+    return out.cpu().numpy()
 
 
 def linear_response(anm, force):
@@ -178,17 +180,21 @@ def linear_response(anm, force):
 
 
 def prs(anm, norm=True):
-    """nma.py:476-531: squared covariance summed over 3x3 blocks."""
+    """nma.py:476-531: perturbation response scanning matrix from the covariance."""
     from .anm import ANM
     if not isinstance(anm, ANM):
         raise ValueError("Instance of ANM class expected.")
     import torch
-    cov = torch.from_numpy(np.ascontiguousarray(anm.covariance)).cuda()
+    from . import _lib
+    if anm._covariance is not None:
+        cov = torch.from_numpy(np.ascontiguousarray(anm._covariance, dtype=np.float64)).cuda()
+    else:
+        lam, modes = _pinv_modes(anm)
+        cov = _engine.modes_covariance(lam, modes)
     n = anm._coord.shape[0]
-    m = (cov * cov).reshape(n, 3, n, 3).sum(dim=(1, 3))
-    if norm:
-        m = m / torch.diagonal(m)[:, None]
-    return m.cpu().numpy()
+    out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.require_device().scb_prs(n, _lib.ptr(cov), int(bool(norm)), _lib.ptr(out), _lib.stream_ptr()))
+    return out.cpu().numpy()
 
 
 def effector_sensor(prs_matrix):

@@ -435,6 +435,16 @@ def test_1l2y_nma_products(structures, key):
     assert np.allclose(prs, ref[f"{key}/anm_prs"], rtol=1e-6)
     assert np.allclose(eff, ref[f"{key}/anm_eff"], rtol=1e-6)
     assert np.allclose(sens, ref[f"{key}/anm_sens"], rtol=1e-6)
+    nm = anm.normal_mode(6, 5.0, 8)
+    want = ref[f"{key}/anm_normal_mode"]
+    sign = np.sign(np.sum(nm[1] * want[1]))          # eigenvector sign is arbitrary
+    assert nm.shape == (8, 20, 3) and np.allclose(sign * nm, want, atol=1e-7)
+    nm = anm.normal_mode(7, 2.0, 6, movement="triangle")
+    want = ref[f"{key}/anm_normal_mode_tri"]
+    sign = np.sign(np.sum(nm[0] * want[0]))
+    assert np.allclose(sign * nm, want, atol=1e-7)
+    with pytest.raises(ValueError):
+        anm.normal_mode(6, 1.0, 4, movement="square")
     with pytest.raises(ValueError):
         anm.mean_square_fluctuation(mode_subset=np.array([5, 6, 7]))
     with pytest.raises(ValueError):
