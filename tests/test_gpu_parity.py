@@ -355,6 +355,45 @@ def test_ensemble_gnm_and_tiny_systems(structures):
     assert np.allclose(res.eigenvalues[1], np.linalg.eigvalsh(H1)[6:26], rtol=EIG_RTOL)
 
 
+def test_ensemble_variants_vs_oracle():
+    """Ensemble path with mass weighting, a patched force field and a distance-dependent one."""
+    n = 200
+    base = orc.synthetic_chain(n, seed=9)
+    res_name, chain_id, res_id = orc.synthetic_sequence(n, seed=9)
+    rng = np.random.default_rng(9)
+    coords = base[None] + rng.normal(0, 0.3, size=(3, n, 3))
+    masses = rng.uniform(60, 190, n)
+    atoms = sc.AtomArray(base, res_name, chain_id, res_id)
+    pair_off = np.array([[0, 1], [50, 51]])
+    pair_on = np.array([[3, 150], [10, 190]])
+    fcs = np.array([5.0, 2.5])
+    cases = [
+        (sc.HinsenForceField(12.0), orc.FFSpec("hinsen", 12.0), masses),
+        (sc.PatchedForceField(sc.TabulatedForceField.e_anm(atoms), contact_pair_off=pair_off, contact_pair_on=pair_on,
+                              force_constants=fcs),
+         None, None),
+        (sc.TabulatedForceField.d_enm(atoms), orc.preset_spec("d_enm", res_name, chain_id, res_id), masses),
+    ]
+    spec_p = orc.preset_spec("e_anm", res_name, chain_id, res_id)
+    spec_p.patched, spec_p.pair_off, spec_p.pair_on, spec_p.pair_on_fc = True, pair_off, pair_on, fcs
+    cases[1] = (cases[1][0], spec_p, None)
+    for ff, spec, m in cases:
+        res = sc.enm_ensemble(coords, ff, k=20, masses=m, return_modes=True)
+        assert res.converged
+        for q in range(len(coords)):
+            H, _ = orc.compute_hessian(coords[q], spec, masses=m)
+            lam, vec = np.linalg.eigh(H)
+            assert np.allclose(res.eigenvalues[q], lam[6:26], rtol=EIG_RTOL, atol=0)
+            assert subspace_sin(res.modes[q], vec.T[6:26]) < ANGLE_TOL
+            want = orc.mean_square_fluctuation(lam, vec.T, 3, mode_subset=np.arange(6, 26))
+            assert np.allclose(res.msf[q], want, rtol=PROD_RTOL, atol=0)
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
+
+
 @pytest.mark.parametrize("key", ["invariant13", "e_anm"])
 def test_7cal_lowest_modes(structures, key):
     """1,776-residue tetramer (test_anm.py:60-84 structure), lowest modes."""
