@@ -104,7 +104,7 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
     // early outer iterations filter in FP32 (see spmm_paired_f32.cu); SCB_FP32=0 disables it
     int allow32 = 1;
     if (const char* env = getenv("SCB_FP32")) allow32 = atoi(env) != 0;
-    const double switch_tol = 2e-3;
+    const double switch_tol = 3e-6;  // x spectrum bound: ~50x above the FP32 stagnation level (~5e-8 * ub)
     if (allow32) SCB_TRY(build_paired32(D, paired_capacity(B, n, P), w.pent, w.pent32, st));
     SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, w.skip32, w.skip64, allow32, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));

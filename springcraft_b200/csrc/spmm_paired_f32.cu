@@ -4,7 +4,7 @@
 // The filter only has to enrich the block in the wanted directions; Rayleigh-Ritz, residuals and the
 // final iterations stay in FP64.  A NumPy prototype on the C3 matrices shows identical outer-iteration
 // counts when the first 5 of 8-9 filters run in FP32 (the FP32 filter stalls at a residual of ~2e-5,
-// the solver switches a structure to the FP64 kernel once its residual is below 2e-3 * theta_k, and the
+// the solver switches a structure to the FP64 kernel once its residual is below 3e-6 * lambda_max (or stops halving), and the
 // converged results are bit-for-bit products of FP64 iterations).  FP32 halves the record and X-row
 // bytes (80-byte records, 128-byte X rows = one LDG.128 per lane and row), halves the registers
 // (32 warps per SM instead of 16) and runs on the 2x wider FP32 pipe.

@@ -441,6 +441,7 @@ __global__ void state_init_kernel(int B, const double* __restrict__ gersh, EigSt
     EigState e;
     e.ub = gersh[s] * (1.0 + 1e-10) + 1e-300;
     e.ub_safe = e.ub;
+    e.prev_res = 0.0;
     e.lo = 0.0;
     e.a0 = 0.0;
     e.iters = 0;
@@ -491,8 +492,12 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
         finished = true;
         atomicSub(n_active, 1);
     }
-    // the FP32 filter stalls near 2e-5 absolute residual: hand over to FP64 well before that
-    const bool use32 = allow32 && !finished && worst > switch_tol * scale;
+    // The FP32 filter stalls at a residual of ~5e-8 * ub (2e-5 on the C3 eANM matrices, 2e-4 on the stiff
+    // sdENM ones): hand over to FP64 at switch_tol * ub, i.e. with a ~50x margin, and also as soon as an FP32
+    // iteration fails to halve the residual.
+    const bool stagnating = e.prev_res > 0.0 && worst > 0.5 * e.prev_res;
+    const bool use32 = allow32 && !finished && worst > switch_tol * e.ub && !stagnating;
+    e.prev_res = worst;
     skip32[s] = (finished || !use32) ? 1 : 0;
     skip64[s] = (finished || use32) ? 1 : 0;
     st[s] = e;

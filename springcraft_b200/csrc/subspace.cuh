@@ -9,6 +9,7 @@ struct EigState {
     double lo;       // lower edge of the damped interval (largest Ritz value of the block)
     double a0;       // lowest Ritz value (scaling point of the filter)
     double ub_safe;  // guaranteed bound (Gershgorin); ub may be a tighter Lanczos estimate
+    double prev_res; // worst wanted residual of the previous outer iteration (FP32 stagnation guard)
     int32_t iters;
     int32_t converged;
 };
