@@ -89,9 +89,9 @@ pair_rows_kernel(int n, int np, int64_t total_pairs, const int64_t* __restrict__
 // ---------------------------------------------------------------------------
 // Y = alpha (H X - c X) - beta W   on the paired format; b = 32 * ncg columns
 // ---------------------------------------------------------------------------
-template <int D>
+template <int D, int BC>
 __global__ void __launch_bounds__(kPairWarps * 32, 1)
-spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __restrict__ rowptr,
+spmm_paired_kernel(int n, int np, int pairs_per_cta, const int64_t* __restrict__ rowptr,
                    const int32_t* __restrict__ pcount, const PairEntry<D>* __restrict__ pent,
                    const double* __restrict__ X, const double* __restrict__ W, double* __restrict__ Y,
                    const double* __restrict__ coef, int coef_stride, const int32_t* __restrict__ done) {
@@ -123,8 +123,9 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __res
     }
     const int t0 = blockIdx.x * pairs_per_cta;
     const int t1 = min(np, t0 + pairs_per_cta);
-    const int ncg = b >> 5;
-    const int rowlen = D * b;            // doubles between the X rows of consecutive nodes
+    constexpr int b = BC;               // compile-time: row offsets become immediates
+    constexpr int ncg = BC >> 5;
+    constexpr int rowlen = D * BC;            // doubles between the X rows of consecutive nodes
     for (int t = t0 + warp; t < t1; t += kPairWarps) {
         const int64_t g = s * np + t;
         const int64_t base = rowptr[s * n + 2 * t] + 2 * g;
@@ -251,17 +252,17 @@ int build_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* col,
     return SCB_OK;
 }
 
-template <int D>
-static int launch_paired(dim3 grid, int n, int np, int per_cta, int b, const int64_t* rowptr, const int32_t* pcount,
+template <int D, int BC>
+static int launch_paired(dim3 grid, int n, int np, int per_cta, const int64_t* rowptr, const int32_t* pcount,
                          const void* pent, const double* X, const double* W, double* Y, const double* coef,
                          int coef_stride, const int32_t* done, cudaStream_t st) {
     const size_t smem = sizeof(PairEntry<D>) * 2 * kPairChunk * kPairWarps + sizeof(uint64_t) * 2 * kPairWarps;
     static bool configured = false;
     if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<D, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    spmm_paired_kernel<D><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, b, rowptr, pcount,
+    spmm_paired_kernel<D, BC><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, rowptr, pcount,
                                                              static_cast<const PairEntry<D>*>(pent), X, W, Y, coef,
                                                              coef_stride, done);
     SCB_LAUNCH_CHECK();
@@ -278,8 +279,10 @@ int spmm_paired(int D, int B, int n, const int64_t* rowptr, const int32_t* pcoun
     per_cta = per_cta < kPairWarps ? kPairWarps : (per_cta > 256 ? 256 : per_cta);
     if (per_cta > np) per_cta = np;
     dim3 grid((unsigned)ceil_div(np, per_cta), (unsigned)B);
-    if (D == 3) return launch_paired<3>(grid, n, np, per_cta, b, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
-    if (D == 1) return launch_paired<1>(grid, n, np, per_cta, b, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
+    if (D == 3 && b == 32) return launch_paired<3, 32>(grid, n, np, per_cta, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
+    if (D == 3 && b == 64) return launch_paired<3, 64>(grid, n, np, per_cta, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
+    if (D == 1 && b == 32) return launch_paired<1, 32>(grid, n, np, per_cta, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
+    if (D == 1 && b == 64) return launch_paired<1, 64>(grid, n, np, per_cta, rowptr, pcount, pent, X, W, Y, coef, coef_stride, done, st);
     return SCB_ERR_INVALID;
 }
 

@@ -50,9 +50,9 @@ block_to_f64_kernel(int64_t per_struct, const float* __restrict__ in, double* __
     reinterpret_cast<double2*>(out + s * per_struct)[q] = make_double2((double)v.x, (double)v.y);
 }
 
-template <int D>
+template <int D, int BC>
 __global__ void __launch_bounds__(kPair32Warps * 32, 1)
-spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* __restrict__ rowptr,
+spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, const int64_t* __restrict__ rowptr,
                        const int32_t* __restrict__ pcount, const PairEntry32<D>* __restrict__ pent,
                        const float* __restrict__ X, const float* __restrict__ W, float* __restrict__ Y,
                        const double* __restrict__ coef, int coef_stride, const int32_t* __restrict__ skip) {
@@ -84,8 +84,9 @@ spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, int b, const int64_t* _
     }
     const int t0 = blockIdx.x * pairs_per_cta;
     const int t1 = min(np, t0 + pairs_per_cta);
-    const int ncg = b >> 5;
-    const int rowlen = D * b;
+    constexpr int b = BC;               // compile-time: row offsets become immediates
+    constexpr int ncg = BC >> 5;
+    constexpr int rowlen = D * BC;
     for (int t = t0 + warp; t < t1; t += kPair32Warps) {
         const int64_t g = s * np + t;
         const int64_t base = rowptr[s * n + 2 * t] + 2 * g;
@@ -209,18 +210,18 @@ int block_to_f64(int B, int64_t per_struct, const float* in, double* out, const 
     return SCB_OK;
 }
 
-template <int D>
-static int launch_paired32(dim3 grid, int n, int np, int per_cta, int b, const int64_t* rowptr,
+template <int D, int BC>
+static int launch_paired32(dim3 grid, int n, int np, int per_cta, const int64_t* rowptr,
                            const int32_t* pcount, const void* pent, const float* X, const float* W, float* Y,
                            const double* coef, int coef_stride, const int32_t* skip, cudaStream_t st) {
     const size_t smem = sizeof(PairEntry32<D>) * 2 * kPairChunk * kPair32Warps + sizeof(uint64_t) * 2 * kPair32Warps;
     static bool configured = false;
     if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_f32_kernel<D, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    spmm_paired_f32_kernel<D><<<grid, kPair32Warps * 32, smem, st>>>(
-        n, np, per_cta, b, rowptr, pcount, static_cast<const PairEntry32<D>*>(pent), X, W, Y, coef, coef_stride, skip);
+    spmm_paired_f32_kernel<D, BC><<<grid, kPair32Warps * 32, smem, st>>>(
+        n, np, per_cta, rowptr, pcount, static_cast<const PairEntry32<D>*>(pent), X, W, Y, coef, coef_stride, skip);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
@@ -235,8 +236,10 @@ int spmm_paired_f32(int D, int B, int n, const int64_t* rowptr, const int32_t* p
     per_cta = per_cta < kPair32Warps ? kPair32Warps : (per_cta > 256 ? 256 : per_cta);
     if (per_cta > np) per_cta = np;
     dim3 grid((unsigned)ceil_div(np, per_cta), (unsigned)B);
-    if (D == 3) return launch_paired32<3>(grid, n, np, per_cta, b, rowptr, pcount, pent32, X, W, Y, coef, coef_stride, skip, st);
-    if (D == 1) return launch_paired32<1>(grid, n, np, per_cta, b, rowptr, pcount, pent32, X, W, Y, coef, coef_stride, skip, st);
+    if (D == 3 && b == 32) return launch_paired32<3, 32>(grid, n, np, per_cta, rowptr, pcount, pent32, X, W, Y, coef, coef_stride, skip, st);
+    if (D == 3 && b == 64) return launch_paired32<3, 64>(grid, n, np, per_cta, rowptr, pcount, pent32, X, W, Y, coef, coef_stride, skip, st);
+    if (D == 1 && b == 32) return launch_paired32<1, 32>(grid, n, np, per_cta, rowptr, pcount, pent32, X, W, Y, coef, coef_stride, skip, st);
+    if (D == 1 && b == 64) return launch_paired32<1, 64>(grid, n, np, per_cta, rowptr, pcount, pent32, X, W, Y, coef, coef_stride, skip, st);
     return SCB_ERR_INVALID;
 }
 
