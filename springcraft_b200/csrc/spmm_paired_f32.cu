@@ -95,11 +95,10 @@ spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, const int64_t* __restri
         for (int cg = 0; cg < ncg; ++cg) {
             const int c0 = cg * 32 + 4 * l8;  // this lane's 4 consecutive columns (16 bytes)
             const float* Xs = X + s * N * b + c0;
-            float acc[R][4];
+            // packed accumulators: acc2[a][0] = columns (c0, c0+1), acc2[a][1] = (c0+2, c0+3); FFMA2 (fma.rn.f32x2)
+            float2 acc2[R][2];
 #pragma unroll
-            for (int a = 0; a < R; ++a)
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) acc[a][cc] = 0.f;
+            for (int a = 0; a < R; ++a) { acc2[a][0] = make_float2(0.f, 0.f); acc2[a][1] = make_float2(0.f, 0.f); }
             __syncwarp();
             if (nchunk > 0 && lane == 0) {
                 const unsigned bytes = (unsigned)(min(kPairChunk, cnt) * sizeof(Entry));
@@ -121,11 +120,12 @@ spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, const int64_t* __restri
 #pragma unroll 2
                 for (int q = slot; q < m; q += 4) {
                     const float* xr = Xs + cur[q].col * rowlen;  // 32-bit offset inside one structure
-                    float x[D][4];
+                    float2 x2[D][2];
 #pragma unroll
                     for (int c = 0; c < D; ++c) {
                         const float4 u = __ldg(reinterpret_cast<const float4*>(xr + c * b));
-                        x[c][0] = u.x; x[c][1] = u.y; x[c][2] = u.z; x[c][3] = u.w;
+                        x2[c][0] = make_float2(u.x, u.y);
+                        x2[c][1] = make_float2(u.z, u.w);
                     }
                     float h[2 * D * D];
                     if (D == 3) {  // 18 floats: 4 x LDS.128 + 1 x LDS.64 (records are 16-byte aligned)
@@ -144,11 +144,18 @@ spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, const int64_t* __restri
 #pragma unroll
                     for (int a = 0; a < R; ++a)
 #pragma unroll
-                        for (int c = 0; c < D; ++c)
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) acc[a][cc] = fmaf(h[a * D + c], x[c][cc], acc[a][cc]);
+                        for (int c = 0; c < D; ++c) {
+                            const float2 hh = make_float2(h[a * D + c], h[a * D + c]);
+                            acc2[a][0] = __ffma2_rn(hh, x2[c][0], acc2[a][0]);
+                            acc2[a][1] = __ffma2_rn(hh, x2[c][1], acc2[a][1]);
+                        }
                 }
                 __syncwarp();
+            }
+            float acc[R][4];
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                acc[a][0] = acc2[a][0].x; acc[a][1] = acc2[a][0].y; acc[a][2] = acc2[a][1].x; acc[a][3] = acc2[a][1].y;
             }
 #pragma unroll
             for (int a = 0; a < R; ++a)
