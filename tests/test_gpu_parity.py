@@ -389,6 +389,35 @@ def test_ensemble_variants_vs_oracle():
             assert np.allclose(res.msf[q], want, rtol=PROD_RTOL, atol=0)
 
 
+def test_degenerate_inputs():
+    """No contacts at all, and structures of 2-3 nodes (edge cases of the contact / assembly kernels)."""
+    rng = np.random.default_rng(1)
+    coord = rng.random((12, 3)) * 100.0
+    K, pairs = sc.compute_kirchhoff(coord, sc.InvariantForceField(0.5))
+    assert pairs.shape == (0, 2) and not K.any()
+    H, pairs = sc.compute_hessian(coord, sc.InvariantForceField(0.5))
+    assert pairs.shape == (0, 2) and H.shape == (36, 36) and not H.any()
+    for n in (2, 3):
+        c = rng.random((n, 3)) * 5.0
+        H, pairs = sc.compute_hessian(c, sc.HinsenForceField())
+        Ho, po = orc.compute_hessian(c, orc.FFSpec("hinsen"))
+        assert np.array_equal(pairs, po) and rel_err(H, Ho) <= HESS_RTOL
+        lam, _ = sc.ANM(c, sc.HinsenForceField()).eigen()
+        assert np.allclose(lam, np.linalg.eigvalsh(Ho), atol=1e-9 * np.abs(Ho).max())
+    with pytest.raises(ValueError):
+        sc.compute_hessian(np.zeros((4, 2)), sc.InvariantForceField(5.0))
+    ca = sc.AtomArray(rng.random((5, 3)), res_name=["ALA"] * 5)
+    with pytest.raises(ValueError):   # natoms mismatch (interaction.py:143-147)
+        sc.compute_hessian(rng.random((6, 3)), sc.TabulatedForceField.e_anm(ca))
+    with pytest.raises(ValueError):   # contact beyond the last bin edge via a patched pair (forcefield.py:526-533)
+        far = rng.random((5, 3)) * 3.0
+        far[4] += 100.0
+        ff = sc.TabulatedForceField.sd_enm(ca)
+        sc.compute_hessian(far, sc.PatchedForceField(sc.InvariantForceField(8.0), contact_pair_on=[[0, 4]],
+                                                     force_constants=[1.0]))
+        ff.force_constant(np.array([0]), np.array([4]), np.array([100.0 ** 2]))
+
+
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()

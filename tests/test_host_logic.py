@@ -213,3 +213,29 @@ def test_atom_array_container():
         sc.AtomArray(np.zeros((3, 2)))
     with pytest.raises(IndexError):
         sc.AtomArray(np.zeros((3, 3)), res_name=["ALA"])
+
+
+def test_read_pdb_ca(tmp_path):
+    """Minimal CA reader (structure input is the step before the path)."""
+    lines = [
+        "MODEL        1",
+        "ATOM      1  N   ASN A   1      -8.901   4.127  -0.555  1.00  0.00           N  ",
+        "ATOM      2  CA  ASN A   1      -8.608   3.135  -1.618  1.00  0.00           C  ",
+        "ATOM      3  CA  LEU A   2      -4.923   4.002  -2.452  1.00  0.00           C  ",
+        "HETATM    4 CA    CA A 101       0.000   0.000   0.000  1.00  0.00          CA  ",
+        "ATOM      5  CA BTYR B   3      -3.690   2.738  -5.833  1.00  0.00           C  ",
+        "ATOM      6  CA  TYR B   3      -3.690   2.738  -5.833  1.00  0.00           C  ",
+        "ENDMDL",
+        "MODEL        2",
+        "ATOM      1  CA  ASN A   1       0.000   0.000   0.000  1.00  0.00           C  ",
+        "ENDMDL",
+    ]
+    path = tmp_path / "mini.pdb"
+    path.write_text("\n".join(lines) + "\n")
+    ca = sc.read_pdb_ca(str(path))
+    assert len(ca) == 3                      # calcium ion and altloc B are skipped, model 1 only
+    assert ca.res_name.tolist() == ["ASN", "LEU", "TYR"] and ca.chain_id.tolist() == ["A", "A", "B"]
+    assert ca.res_id.tolist() == [1, 2, 3] and ca.coord.dtype == np.float32
+    assert np.allclose(ca.coord[1], [-4.923, 4.002, -2.452])
+    ff = sc.TabulatedForceField.e_anm(ca)
+    assert ff.natoms == 3 and ff._bonded_next.tolist() == [1, 0, 0]
