@@ -106,7 +106,7 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
     if (const char* env = getenv("SCB_FP32")) allow32 = atoi(env) != 0;
     const double switch_tol = 3e-6;  // x spectrum bound: ~50x above the FP32 stagnation level (~5e-8 * ub)
     if (allow32) SCB_TRY(build_paired32(D, paired_capacity(B, n, P), w.pent, w.pent32, st));
-    SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, w.skip32, w.skip64, allow32, st));
+    SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, w.skip32, w.skip64, allow32, degree, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
     SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
 
@@ -184,7 +184,7 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         if ((status = zero_active_rn2(B, b, w.rn2, done, st)) != SCB_OK) break;
         if ((status = residual_norms(B, N, b, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
         if ((status = state_update(B, b, k, tol, w.theta, w.rn2, w.state, w.done, w.n_active, resid, w.skip32,
-                                   w.skip64, allow32, switch_tol, st)) != SCB_OK)
+                                   w.skip64, allow32, switch_tol, degree, st)) != SCB_OK)
             break;
         if (cudaMemcpyAsync(h_active, w.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {

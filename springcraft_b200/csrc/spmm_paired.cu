@@ -126,6 +126,18 @@ spmm_paired_kernel(int n, int np, int pairs_per_cta, const int64_t* __restrict__
     constexpr int b = BC;               // compile-time: row offsets become immediates
     constexpr int ncg = BC >> 5;
     constexpr int rowlen = D * BC;            // doubles between the X rows of consecutive nodes
+    if (coef && alpha == 0.0) {
+        // idle filter step of a structure that runs fewer degrees: carry its rows forward, Y = X
+        for (int t = t0 + warp; t < t1; t += kPairWarps)
+            for (int a = 0; a < R; ++a) {
+                const int64_t r = (int64_t)D * 2 * t + a;
+                if (r >= N) continue;
+                const double* src = X + (s * N + r) * b;
+                double* dst = Y + (s * N + r) * b;
+                for (int q = lane; q < b; q += 32) dst[q] = src[q];
+            }
+        return;
+    }
     for (int t = t0 + warp; t < t1; t += kPairWarps) {
         const int64_t g = s * np + t;
         const int64_t base = rowptr[s * n + 2 * t] + 2 * g;

@@ -87,6 +87,18 @@ spmm_paired_f32_kernel(int n, int np, int pairs_per_cta, const int64_t* __restri
     constexpr int b = BC;               // compile-time: row offsets become immediates
     constexpr int ncg = BC >> 5;
     constexpr int rowlen = D * BC;
+    if (coef && alpha == 0.f) {
+        // idle filter step (see spmm_paired.cu): Y = X
+        for (int t = t0 + warp; t < t1; t += kPair32Warps)
+            for (int a = 0; a < R; ++a) {
+                const int64_t r = (int64_t)D * 2 * t + a;
+                if (r >= N) continue;
+                const float* src = X + (s * N + r) * b;
+                float* dst = Y + (s * N + r) * b;
+                for (int q = lane; q < b; q += 32) dst[q] = src[q];
+            }
+        return;
+    }
     for (int t = t0 + warp; t < t1; t += kPair32Warps) {
         const int64_t g = s * np + t;
         const int64_t base = rowptr[s * n + 2 * t] + 2 * g;

@@ -434,7 +434,7 @@ int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, c
 // solver state
 // ---------------------------------------------------------------------------
 __global__ void state_init_kernel(int B, const double* __restrict__ gersh, EigState* st, int32_t* done,
-                                  int32_t* n_active, int32_t* skip32, int32_t* skip64, int allow32) {
+                                  int32_t* n_active, int32_t* skip32, int32_t* skip64, int allow32, int degree) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) *n_active = B;
     if (s >= B) return;
@@ -446,6 +446,8 @@ __global__ void state_init_kernel(int B, const double* __restrict__ gersh, EigSt
     e.a0 = 0.0;
     e.iters = 0;
     e.converged = 0;
+    e.degree_next = degree;
+    e.degree_used = degree;
     st[s] = e;
     done[s] = 0;
     // filter precision of the next outer iteration: FP32 first (when allowed), FP64 later
@@ -463,7 +465,7 @@ __global__ void zero_active_rn2_kernel(int B, int b, double* rn2, const int32_t*
 __global__ void state_update_kernel(int B, int b, int k, double tol, const double* __restrict__ theta,
                                     const double* __restrict__ rn2, EigState* st, int32_t* done,
                                     int32_t* n_active, double* __restrict__ resid, int32_t* skip32,
-                                    int32_t* skip64, int allow32, double switch_tol) {
+                                    int32_t* skip64, int allow32, double switch_tol, int degree) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= B || done[s]) return;
     const double* th = theta + (int64_t)s * b;
@@ -497,6 +499,17 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
     // iteration fails to halve the residual.
     const bool stagnating = e.prev_res > 0.0 && worst > 0.5 * e.prev_res;
     const bool use32 = allow32 && !finished && worst > switch_tol * e.ub && !stagnating;
+    // Last iterations: a full-degree filter overshoots the tolerance.  From the reduction per degree observed
+    // in the iteration just finished, pick the smallest degree that is predicted to reach 0.3 * tol.
+    int next_degree = degree;
+    if (!use32 && !finished && e.prev_res > 0.0 && worst < 0.5 * e.prev_res && e.iters > 2) {
+        const double log_rho = log(worst / e.prev_res) / (double)max(e.degree_used, 1);   // < 0
+        const double need = log(0.3 * tol * scale / worst);                                 // < 0
+        const int d = (int)ceil(need / log_rho) + 1;
+        next_degree = min(degree, max(8, d));
+    }
+    e.degree_used = next_degree;   // the coming iteration runs next_degree steps
+    e.degree_next = next_degree;
     e.prev_res = worst;
     skip32[s] = (finished || !use32) ? 1 : 0;
     skip64[s] = (finished || use32) ? 1 : 0;
@@ -513,8 +526,13 @@ __global__ void cheb_coef_kernel(int B, int degree, const EigState* __restrict__
     const double sigma1 = half / (e.a0 - c);
     double sigma = sigma1;
     double* cf = coef + (int64_t)s * degree * 3;
-    cf[0] = sigma1 / half; cf[1] = c; cf[2] = 0.0;
-    for (int d = 1; d < degree; ++d) {
+    // a structure that needs only deg_s < degree steps idles through the first (degree - deg_s) launches:
+    // alpha == 0 tells the SpMM kernel to copy its rows forward (Y = X) so that buffer parity stays common
+    const int deg_s = min(max(e.degree_next, 2), degree);
+    const int start = degree - deg_s;
+    for (int d = 0; d < start; ++d) { cf[3 * d] = 0.0; cf[3 * d + 1] = 0.0; cf[3 * d + 2] = 0.0; }
+    cf[3 * start] = sigma1 / half; cf[3 * start + 1] = c; cf[3 * start + 2] = 0.0;
+    for (int d = start + 1; d < degree; ++d) {
         const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
         cf[3 * d] = 2.0 * sigma2 / half;
         cf[3 * d + 1] = c;
@@ -537,8 +555,9 @@ __global__ void gather_results_kernel(int B, int b, const double* __restrict__ t
 }
 
 int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, int32_t* skip32,
-               int32_t* skip64, int allow32, cudaStream_t s) {
-    state_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, s>>>(B, gersh, st, done, n_active, skip32, skip64, allow32);
+               int32_t* skip64, int allow32, int degree, cudaStream_t s) {
+    state_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, s>>>(B, gersh, st, done, n_active, skip32, skip64, allow32,
+                                                                 degree);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
@@ -549,9 +568,9 @@ int zero_active_rn2(int B, int b, double* rn2, const int32_t* done, cudaStream_t
 }
 int state_update(int B, int b, int k, double tol, const double* theta, const double* rn2, EigState* st,
                  int32_t* done, int32_t* n_active, double* resid, int32_t* skip32, int32_t* skip64, int allow32,
-                 double switch_tol, cudaStream_t s) {
+                 double switch_tol, int degree, cudaStream_t s) {
     state_update_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, b, k, tol, theta, rn2, st, done, n_active, resid,
-                                                                  skip32, skip64, allow32, switch_tol);
+                                                                  skip32, skip64, allow32, switch_tol, degree);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }

@@ -12,6 +12,8 @@ struct EigState {
     double prev_res; // worst wanted residual of the previous outer iteration (FP32 stagnation guard)
     int32_t iters;
     int32_t converged;
+    int32_t degree_next;  // filter degree of the next outer iteration (<= the launch degree; last iterations shrink)
+    int32_t degree_used;
 };
 
 int spmm_cheb(int D, int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
@@ -41,11 +43,11 @@ int deflate(int B, int64_t N, int b, int nz, const double* Z, double* X, double*
 int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, const double* theta, double* rn2,
                    const int32_t* done, cudaStream_t st);
 int state_init(int B, const double* gersh, EigState* st, int32_t* done, int32_t* n_active, int32_t* skip32,
-               int32_t* skip64, int allow32, cudaStream_t s);
+               int32_t* skip64, int allow32, int degree, cudaStream_t s);
 int zero_active_rn2(int B, int b, double* rn2, const int32_t* done, cudaStream_t s);
 int state_update(int B, int b, int k, double tol, const double* theta, const double* rn2, EigState* st,
                  int32_t* done, int32_t* n_active, double* resid, int32_t* skip32, int32_t* skip64, int allow32,
-                 double switch_tol, cudaStream_t s);
+                 double switch_tol, int degree, cudaStream_t s);
 int cheb_coef(int B, int degree, const EigState* st, const int32_t* done, double* coef, cudaStream_t s);
 int rand_init(int64_t total, uint64_t seed, double* X, cudaStream_t s);
 int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st);
