@@ -69,7 +69,13 @@ class DenseRowOperator:
             _lib.ptr(local), b, int(coeffs is not None), float(alpha), float(cshift), float(beta), _lib.stream_ptr()))
         if self.world == 1:
             return local
-        # all-gather of the row slabs (node granularity so that ragged splits stay aligned)
+        if self.n % self.world == 0:
+            # equal slabs: one NCCL all-gather straight into the full block (rows are rank-major contiguous)
+            import torch.distributed as dist
+            full = torch.empty((self.N, b), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(full, local)
+            return full
+        # ragged split: all-gather of padded slabs (node granularity keeps the slabs aligned)
         full = gather_results(local.view(self.row1 - self.row0, self.D * b), self.n, dim=0)
         return full.view(self.N, b)
 
