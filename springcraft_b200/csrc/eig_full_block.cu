@@ -5,9 +5,14 @@
 // The matrix is cut into column blocks of width 32.  A round-robin tournament
 // pairs the blocks; for each pair (I,J) the 64x64 pivot sub-matrix is fully
 // diagonalised in shared memory by cyclic Jacobi (one CTA per pair), giving an
-// orthogonal R.  The update A <- R^T A R, V <- V R is applied as two batched
-// passes of 64x64x64 tile products on the FP64 tensor cores (DMMA m8n8k4):
-// all row pairs first, then all column pairs (pairs are disjoint inside a step).
+// orthogonal R.  The update A <- R^T A R, V <- V R is applied by ONE launch of
+// 64x64x64 tile products on the FP64 tensor cores (DMMA m8n8k4): the pairs of a
+// step are disjoint, so tile (k,l) of A (rows of pair k, columns of pair l) is
+// A_kl <- R_k^T A_kl R_l independently of all other tiles; only k <= l is
+// computed and mirrored (A stays exactly symmetric), V tiles need one product.
+// Step 0 of a sweep rotates every index pair inside its pivots, the other
+// steps only the pairs ACROSS the two blocks, i.e. each index pair is rotated
+// once per sweep (cyclic-by-blocks ordering).
 // Sweeps repeat until the off-diagonal Frobenius norm is ~1e-14 of the total.
 #include <stdlib.h>
 
@@ -54,7 +59,7 @@ __global__ void bj_init_kernel(int N, int Np, const double* __restrict__ A, doub
 // one CTA per block pair: diagonalise the 64x64 pivot, write R[pair][64][64]
 __global__ void __launch_bounds__(256)
 bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double* __restrict__ R,
-                int32_t* __restrict__ active, int inner_sweeps) {
+                int32_t* __restrict__ active, int inner_sweeps, int cross_only) {
     constexpr int LD = kPW + 1;
     extern __shared__ double sm[];
     double* S = sm;
@@ -68,8 +73,18 @@ bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double*
         const int r = q / kPW, c = q % kPW;
         const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
         const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
-        S[r * LD + c] = 0.5 * (Ap[(int64_t)gr * Np + gc] + Ap[(int64_t)gc * Np + gr]);
+        S[r * LD + c] = Ap[(int64_t)gr * Np + gc];  // A is kept exactly symmetric by the update kernel
         V[r * LD + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // the diagonal tile is symmetric up to rounding only: average the two triangles
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        const int r = q / kPW, c = q % kPW;
+        if (r < c) {
+            const double a = 0.5 * (S[r * LD + c] + S[c * LD + r]);
+            S[r * LD + c] = a;
+            S[c * LD + r] = a;
+        }
     }
     __syncthreads();
     // skip pivots whose coupling block is already negligible
@@ -84,9 +99,13 @@ bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double*
     const bool work = off > 1e-32 * dg && off > 0.0;
     // inexact pivot diagonalisation: a few cyclic sweeps per visit are enough for the outer iteration to
     // converge (quadratically at the end) and cost 5x less than a full inner solve
-    if (work) jacobi_eigen_smem<LD>(S, V, kPW, cs, sn, pp, qq, red, kPW, inner_sweeps);
-    double* Rp = R + (int64_t)blockIdx.x * kPW * kPW;
-    for (int q = tid; q < kPW * kPW; q += 256) Rp[q] = V[(q / kPW) * LD + q % kPW];
+    if (work) jacobi_eigen_smem<kPW, LD>(S, V, cs, sn, pp, qq, red, inner_sweeps, cross_only != 0);
+    // R and R^T (the update kernel wants both row-major)
+    double* Rp = R + (int64_t)blockIdx.x * 2 * kPW * kPW;
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        Rp[q] = V[(q / kPW) * LD + q % kPW];
+        Rp[kPW * kPW + q] = V[(q % kPW) * LD + q / kPW];
+    }
     if (tid == 0) active[blockIdx.x] = work ? 1 : 0;
 }
 
@@ -112,68 +131,89 @@ __device__ __forceinline__ void tile_product(const double* sL, const double* sR,
     }
 }
 
-// rows pass: [A_I,: ; A_J,:] <- R^T [A_I,: ; A_J,:]   grid (Np/64 column tiles, pairs)
-__global__ void __launch_bounds__(256)
-bj_rows_kernel(int Np, int nb, int step, double* __restrict__ Ap, const double* __restrict__ R,
-               const int32_t* __restrict__ active) {
-    extern __shared__ double sm[];
-    double* sL = sm;               // R^T
-    double* sR = sm + kPW * kTLD;  // the 64 x 64 tile of A
-    if (!active[blockIdx.y]) return;
-    int I, J;
-    block_pair(nb, step, blockIdx.y, &I, &J);
-    const double* Rp = R + (int64_t)blockIdx.y * kPW * kPW;
-    const int c0 = blockIdx.x * kPW;
-    const int tid = threadIdx.x;
-    for (int q = tid; q < kPW * kPW; q += 256) {
-        const int r = q / kPW, c = q % kPW;
-        sL[c * kTLD + r] = Rp[q];  // transpose
-        const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
-        sR[r * kTLD + c] = Ap[(int64_t)gr * Np + c0 + c];
-    }
-    __syncthreads();
-    double acc[8][2];
-    tile_product(sL, sR, acc);
-    const int lane = tid & 31, warp = tid >> 5;
-    const int r = warp * 8 + (lane >> 2);
-    const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j * 8 + 2 * (lane & 3);
-        *reinterpret_cast<double2*>(&Ap[(int64_t)gr * Np + c]) = make_double2(acc[j][0], acc[j][1]);
-    }
-}
+__device__ __forceinline__ int pair_index(int I, int J, int r) { return r < kBW ? I * kBW + r : J * kBW + r - kBW; }
 
-// columns pass: [M_:,I M_:,J] <- [M_:,I M_:,J] R for M = A (z=0) and M = V (z=1)
+// One launch per step.  CTAs [0, nA): tiles k <= l of A, A_kl <- R_k^T A_kl R_l, mirrored into A_lk.
+// CTAs [nA, nA + (Np/64) * npairs): V[64 rows][columns of pair l] <- (same) R_l.
 __global__ void __launch_bounds__(256)
-bj_cols_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __restrict__ V,
-               const double* __restrict__ R, const int32_t* __restrict__ active) {
+bj_update_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __restrict__ V,
+                 const double* __restrict__ R, const int32_t* __restrict__ active) {
+    constexpr int TLD = kPW + 1;   // transposition buffer: odd leading dimension
     extern __shared__ double sm[];
-    double* sL = sm;               // 64 rows x (I,J) columns
-    double* sR = sm + kPW * kTLD;  // R
-    if (!active[blockIdx.y]) return;
-    int I, J;
-    block_pair(nb, step, blockIdx.y, &I, &J);
-    double* M = blockIdx.z ? V : Ap;
-    const double* Rp = R + (int64_t)blockIdx.y * kPW * kPW;
-    const int r0 = blockIdx.x * kPW;
-    const int tid = threadIdx.x;
+    double* sL = sm;                    // left factor (R_k^T, then the mirror staging buffer)
+    double* sM = sm + kPW * kTLD;       // the tile (then T = R_k^T A_kl)
+    double* sR = sm + 2 * kPW * kTLD;   // right factor R_l
+    const int npairs = nb / 2;
+    const int nA = npairs * (npairs + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[8][2];
+    if ((int)blockIdx.x >= nA) {
+        const int v = blockIdx.x - nA;
+        const int r0 = (v / npairs) * kPW, l = v % npairs;
+        if (!active[l]) return;
+        int I, J;
+        block_pair(nb, step, l, &I, &J);
+        const double* Rl = R + (int64_t)l * 2 * kPW * kPW;
+        for (int q = tid; q < kPW * kPW; q += 256) {
+            const int r = q / kPW, c = q % kPW;
+            sR[r * kTLD + c] = Rl[q];
+            sM[r * kTLD + c] = V[(int64_t)(r0 + r) * Np + pair_index(I, J, c)];
+        }
+        __syncthreads();
+        tile_product(sM, sR, acc);
+        const int r = r0 + warp * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = j * 8 + 2 * (lane & 3);
+            *reinterpret_cast<double2*>(&V[(int64_t)r * Np + pair_index(I, J, c)]) = make_double2(acc[j][0], acc[j][1]);
+        }
+        return;
+    }
+    int t = blockIdx.x, k = 0;
+    while (t >= npairs - k) { t -= npairs - k; ++k; }
+    const int l = k + t;
+    if (!active[k] && !active[l]) return;
+    int Ik, Jk, Il, Jl;
+    block_pair(nb, step, k, &Ik, &Jk);
+    block_pair(nb, step, l, &Il, &Jl);
+    const double* RkT = R + (int64_t)k * 2 * kPW * kPW + kPW * kPW;
+    const double* Rl = R + (int64_t)l * 2 * kPW * kPW;
     for (int q = tid; q < kPW * kPW; q += 256) {
         const int r = q / kPW, c = q % kPW;
-        sR[r * kTLD + c] = Rp[q];
-        const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
-        sL[r * kTLD + c] = M[(int64_t)(r0 + r) * Np + gc];
+        sL[r * kTLD + c] = RkT[q];
+        sR[r * kTLD + c] = Rl[q];
+        sM[r * kTLD + c] = Ap[(int64_t)pair_index(Ik, Jk, r) * Np + pair_index(Il, Jl, c)];
     }
     __syncthreads();
-    double acc[8][2];
-    tile_product(sL, sR, acc);
-    const int lane = tid & 31, warp = tid >> 5;
-    const int r = r0 + warp * 8 + (lane >> 2);
+    tile_product(sL, sM, acc);   // T = R_k^T A_kl
+    __syncthreads();
+    {
+        const int r = warp * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<double2*>(&sM[r * kTLD + j * 8 + 2 * (lane & 3)]) = make_double2(acc[j][0], acc[j][1]);
+    }
+    __syncthreads();
+    tile_product(sM, sR, acc);   // A_kl' = T R_l
+    const int r = warp * 8 + (lane >> 2);
+    const int gr = pair_index(Ik, Jk, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = j * 8 + 2 * (lane & 3);
-        const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
-        *reinterpret_cast<double2*>(&M[(int64_t)r * Np + gc]) = make_double2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<double2*>(&Ap[(int64_t)gr * Np + pair_index(Il, Jl, c)]) = make_double2(acc[j][0], acc[j][1]);
+    }
+    if (k == l) return;
+    // mirror: A_lk = (A_kl')^T, transposed through shared memory (sL is free: product 1 is complete)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = j * 8 + 2 * (lane & 3);
+        sL[r * TLD + c] = acc[j][0];
+        sL[r * TLD + c + 1] = acc[j][1];
+    }
+    __syncthreads();
+    for (int q = tid; q < kPW * kPW; q += 256) {
+        const int rr = q / kPW, cc = q % kPW;   // element (rr, cc) of A_lk = element (cc, rr) of A_kl'
+        Ap[(int64_t)pair_index(Il, Jl, rr) * Np + pair_index(Ik, Jk, cc)] = sL[cc * TLD + rr];
     }
 }
 
@@ -243,7 +283,7 @@ static void bj_carve(Arena& ar, BjWork* w, int N) {
     const int nb = Np / kBW;
     w->Ap = ar.take<double>((size_t)Np * Np);
     w->V = ar.take<double>((size_t)Np * Np);
-    w->R = ar.take<double>((size_t)(nb / 2) * kPW * kPW);
+    w->R = ar.take<double>((size_t)(nb / 2) * 2 * kPW * kPW);
     w->norms = ar.take<double>(2);
     w->active = ar.take<int32_t>(nb / 2);
     w->rank = ar.take<int32_t>(N);
@@ -267,16 +307,17 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
     const int nb = Np / kBW;
     const int npairs = nb / 2;
     const size_t smem_pivot = sizeof(double) * 2 * kPW * (kPW + 1);
-    const size_t smem_tile = sizeof(double) * 2 * kPW * kTLD;
+    const size_t smem_tile = sizeof(double) * 3 * kPW * kTLD;
     static bool configured = false;
     if (!configured) {
         SCB_CUDA(cudaFuncSetAttribute(bj_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pivot));
-        SCB_CUDA(cudaFuncSetAttribute(bj_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
-        SCB_CUDA(cudaFuncSetAttribute(bj_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+        SCB_CUDA(cudaFuncSetAttribute(bj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
         configured = true;
     }
     int inner_sweeps = 1;
     if (const char* env = getenv("SCB_BJ_INNER")) inner_sweeps = atoi(env) > 0 ? atoi(env) : inner_sweeps;
+    int cross = 1;
+    if (const char* env = getenv("SCB_BJ_CROSS")) cross = atoi(env);
     double* h_norms = nullptr;
     SCB_CUDA(cudaMallocHost(&h_norms, 2 * sizeof(double)));
     int status = SCB_OK;
@@ -287,11 +328,13 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
         bool converged = false;
         for (int sweep = 0; sweep < 60 && !converged; ++sweep) {
             for (int step = 0; step < nb - 1; ++step) {
-                bj_pivot_kernel<<<npairs, 256, smem_pivot, st>>>(Np, nb, step, w.Ap, w.R, w.active, inner_sweeps);
-                bj_rows_kernel<<<dim3(Np / kPW, npairs), 256, smem_tile, st>>>(Np, nb, step, w.Ap, w.R, w.active);
-                bj_cols_kernel<<<dim3(Np / kPW, npairs, 2), 256, smem_tile, st>>>(Np, nb, step, w.Ap, w.V, w.R,
-                                                                                 w.active);
-                count_launches(3);
+                // step 0 of a sweep rotates every pair inside its 64x64 pivots (this covers the pairs inside each
+                // diagonal block once per sweep); the other steps only rotate pairs ACROSS the two blocks
+                bj_pivot_kernel<<<npairs, 256, smem_pivot, st>>>(Np, nb, step, w.Ap, w.R, w.active, inner_sweeps,
+                                                                 (cross && step > 0) ? 1 : 0);
+                bj_update_kernel<<<npairs * (npairs + 1) / 2 + (Np / kPW) * npairs, 256, smem_tile, st>>>(
+                    Np, nb, step, w.Ap, w.V, w.R, w.active);
+                count_launches(2);
             }
             cudaMemsetAsync(w.norms, 0, 2 * sizeof(double), st);
             bj_norms_kernel<<<4 * kNumSM, 256, 0, st>>>(Np, w.Ap, w.norms);

@@ -171,7 +171,7 @@ rr_kernel(const double* __restrict__ Sg, const double* __restrict__ Tg, double* 
     __syncthreads();
     for (int q = tid; q < BW * BW; q += 256) V[(q / BW) * LD + q % BW] = (q / BW == q % BW) ? 1.0 : 0.0;
     __syncthreads();
-    jacobi_eigen_smem<LD>(T, V, BW, cs, sn, pp, qq, red, BW);
+    jacobi_eigen_smem<BW, LD>(T, V, cs, sn, pp, qq, red);
     // ascending order (ties broken by index)
     if (tid < BW) ev[tid] = T[tid * LD + tid];
     __syncthreads();
