@@ -56,29 +56,32 @@ __global__ void bj_init_kernel(int N, int Np, const double* __restrict__ A, doub
     V[q] = (i == j) ? 1.0 : 0.0;
 }
 
-// one CTA per block pair: diagonalise the 64x64 pivot, write R[pair][64][64]
-__global__ void __launch_bounds__(256)
+// one CTA per block pair: diagonalise the 64x64 pivot, write R and R^T [pair][2][64][64]
+constexpr int kPivotThreads = 512;
+
+__global__ void __launch_bounds__(kPivotThreads)
 bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double* __restrict__ R,
                 int32_t* __restrict__ active, int inner_sweeps, int cross_only) {
     constexpr int LD = kPW + 1;
+    constexpr int NT = kPivotThreads;
     extern __shared__ double sm[];
     double* S = sm;
     double* V = S + kPW * LD;
-    __shared__ double cs[kPW / 2], sn[kPW / 2], red[8];
-    __shared__ int pp[kPW / 2], qq[kPW / 2];
+    __shared__ double cs[kPW], sn[kPW], red[NT / 32];   // two rotation-parameter sets of kPW/2
+    __shared__ int pp[kPW], qq[kPW];
     int I, J;
     block_pair(nb, step, blockIdx.x, &I, &J);
     const int tid = threadIdx.x;
-    for (int q = tid; q < kPW * kPW; q += 256) {
+    for (int q = tid; q < kPW * kPW; q += NT) {
         const int r = q / kPW, c = q % kPW;
         const int gr = (r < kBW ? I * kBW + r : J * kBW + r - kBW);
         const int gc = (c < kBW ? I * kBW + c : J * kBW + c - kBW);
-        S[r * LD + c] = Ap[(int64_t)gr * Np + gc];  // A is kept exactly symmetric by the update kernel
+        S[r * LD + c] = Ap[(int64_t)gr * Np + gc];
         V[r * LD + c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
     // the diagonal tile is symmetric up to rounding only: average the two triangles
-    for (int q = tid; q < kPW * kPW; q += 256) {
+    for (int q = tid; q < kPW * kPW; q += NT) {
         const int r = q / kPW, c = q % kPW;
         if (r < c) {
             const double a = 0.5 * (S[r * LD + c] + S[c * LD + r]);
@@ -89,20 +92,19 @@ bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double*
     __syncthreads();
     // skip pivots whose coupling block is already negligible
     double off = 0.0, dg = 0.0;
-    for (int q = tid; q < kPW * kPW; q += 256) {
+    for (int q = tid; q < kPW * kPW; q += NT) {
         const int r = q / kPW, c = q % kPW;
         const double v = S[r * LD + c];
         if (r == c) dg += v * v; else off += v * v;
     }
-    off = bj_block_sum(off, red);
-    dg = bj_block_sum(dg, red);
+    off = block_sum_nt<NT>(off, red);
+    dg = block_sum_nt<NT>(dg, red);
     const bool work = off > 1e-32 * dg && off > 0.0;
-    // inexact pivot diagonalisation: a few cyclic sweeps per visit are enough for the outer iteration to
-    // converge (quadratically at the end) and cost 5x less than a full inner solve
-    if (work) jacobi_eigen_smem<kPW, LD>(S, V, cs, sn, pp, qq, red, inner_sweeps, cross_only != 0);
-    // R and R^T (the update kernel wants both row-major)
+    // inexact pivot diagonalisation: ONE cyclic sweep per visit is enough for the outer iteration to converge
+    // (quadratically at the end) and costs 5x less than a full inner solve
+    if (work) jacobi_eigen_smem<kPW, LD, NT>(S, V, cs, sn, pp, qq, red, inner_sweeps, cross_only != 0);
     double* Rp = R + (int64_t)blockIdx.x * 2 * kPW * kPW;
-    for (int q = tid; q < kPW * kPW; q += 256) {
+    for (int q = tid; q < kPW * kPW; q += NT) {
         Rp[q] = V[(q / kPW) * LD + q % kPW];
         Rp[kPW * kPW + q] = V[(q % kPW) * LD + q / kPW];
     }
@@ -131,6 +133,11 @@ __device__ __forceinline__ void tile_product(const double* sL, const double* sR,
     }
 }
 
+__device__ __forceinline__ void bj_cp_async16(void* smem, const void* gmem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+
 __device__ __forceinline__ int pair_index(int I, int J, int r) { return r < kBW ? I * kBW + r : J * kBW + r - kBW; }
 
 // One launch per step.  CTAs [0, nA): tiles k <= l of A, A_kl <- R_k^T A_kl R_l, mirrored into A_lk.
@@ -154,11 +161,13 @@ bj_update_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __re
         int I, J;
         block_pair(nb, step, l, &I, &J);
         const double* Rl = R + (int64_t)l * 2 * kPW * kPW;
-        for (int q = tid; q < kPW * kPW; q += 256) {
-            const int r = q / kPW, c = q % kPW;
-            sR[r * kTLD + c] = Rl[q];
-            sM[r * kTLD + c] = V[(int64_t)(r0 + r) * Np + pair_index(I, J, c)];
+        for (int q = tid; q < kPW * kPW / 2; q += 256) {
+            const int r = q / (kPW / 2), c = 2 * (q % (kPW / 2));
+            bj_cp_async16(&sR[r * kTLD + c], &Rl[r * kPW + c]);
+            bj_cp_async16(&sM[r * kTLD + c], &V[(int64_t)(r0 + r) * Np + pair_index(I, J, c)]);
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();
         tile_product(sM, sR, acc);
         const int r = r0 + warp * 8 + (lane >> 2);
@@ -178,14 +187,22 @@ bj_update_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __re
     block_pair(nb, step, l, &Il, &Jl);
     const double* RkT = R + (int64_t)k * 2 * kPW * kPW + kPW * kPW;
     const double* Rl = R + (int64_t)l * 2 * kPW * kPW;
-    for (int q = tid; q < kPW * kPW; q += 256) {
-        const int r = q / kPW, c = q % kPW;
-        sL[r * kTLD + c] = RkT[q];
-        sR[r * kTLD + c] = Rl[q];
-        sM[r * kTLD + c] = Ap[(int64_t)pair_index(Ik, Jk, r) * Np + pair_index(Il, Jl, c)];
+    // asynchronous 16-byte copies: {R_k^T, A_kl} first, R_l lands while the first product runs
+    for (int q = tid; q < kPW * kPW / 2; q += 256) {
+        const int r = q / (kPW / 2), c = 2 * (q % (kPW / 2));
+        bj_cp_async16(&sL[r * kTLD + c], &RkT[r * kPW + c]);
+        bj_cp_async16(&sM[r * kTLD + c], &Ap[(int64_t)pair_index(Ik, Jk, r) * Np + pair_index(Il, Jl, c)]);
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+    for (int q = tid; q < kPW * kPW / 2; q += 256) {
+        const int r = q / (kPW / 2), c = 2 * (q % (kPW / 2));
+        bj_cp_async16(&sR[r * kTLD + c], &Rl[r * kPW + c]);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 1;\n" ::);
     __syncthreads();
     tile_product(sL, sM, acc);   // T = R_k^T A_kl
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
     {
         const int r = warp * 8 + (lane >> 2);
@@ -330,7 +347,7 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
             for (int step = 0; step < nb - 1; ++step) {
                 // step 0 of a sweep rotates every pair inside its 64x64 pivots (this covers the pairs inside each
                 // diagonal block once per sweep); the other steps only rotate pairs ACROSS the two blocks
-                bj_pivot_kernel<<<npairs, 256, smem_pivot, st>>>(Np, nb, step, w.Ap, w.R, w.active, inner_sweeps,
+                bj_pivot_kernel<<<npairs, kPivotThreads, smem_pivot, st>>>(Np, nb, step, w.Ap, w.R, w.active, inner_sweeps,
                                                                  (cross && step > 0) ? 1 : 0);
                 bj_update_kernel<<<npairs * (npairs + 1) / 2 + (Np / kPW) * npairs, 256, smem_tile, st>>>(
                     Np, nb, step, w.Ap, w.V, w.R, w.active);

@@ -90,8 +90,8 @@ rr_kernel(const double* __restrict__ Sg, const double* __restrict__ Tg, double* 
     double* S = sm;
     double* T = S + BW * LD;
     double* V = T + BW * LD;
-    __shared__ double cs[BW / 2], sn[BW / 2], red[8], ev[BW];
-    __shared__ int pp[BW / 2], qq[BW / 2], rank[BW];
+    __shared__ double cs[BW], sn[BW], red[8], ev[BW];   // two rotation-parameter sets of BW/2
+    __shared__ int pp[BW], qq[BW], rank[BW];
     const int s = blockIdx.x;
     if (done && done[s]) return;
     const int tid = threadIdx.x;
@@ -171,7 +171,7 @@ rr_kernel(const double* __restrict__ Sg, const double* __restrict__ Tg, double* 
     __syncthreads();
     for (int q = tid; q < BW * BW; q += 256) V[(q / BW) * LD + q % BW] = (q / BW == q % BW) ? 1.0 : 0.0;
     __syncthreads();
-    jacobi_eigen_smem<BW, LD>(T, V, cs, sn, pp, qq, red);
+    jacobi_eigen_smem<BW, LD, 256>(T, V, cs, sn, pp, qq, red);
     // ascending order (ties broken by index)
     if (tid < BW) ev[tid] = T[tid * LD + tid];
     __syncthreads();
