@@ -193,6 +193,22 @@ int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t *rowptr, const 
 int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const double *slab,
                          const double *X, const double *W, double *Y, int b, int fused,
                          double alpha, double cshift, double beta, void *stream);
+/* Same product with the all-gather of the row slabs fused into the epilogue: Y_all is a HOST array of
+ * `world` device pointers, Y_all[p] = the full [N][b] output block of rank p mapped into this process
+ * (scb_peer_open; the entry of this rank is its own scb_peer_alloc buffer).  Rows [row0,row1) are stored
+ * into every block over NVLink peer memory; the caller runs a barrier collective before any rank reads
+ * its block (replaces ncclAllGather of SURVEY 8e C4).  world <= 16; X, W must not alias an output. */
+int scb_dense_slab_apply_allgather(int64_t N, int64_t row0, int64_t row1, const double *slab,
+                                   const double *X, const double *W, double *const *Y_all, int world,
+                                   int b, int fused, double alpha, double cshift, double beta,
+                                   void *stream);
+/* Peer-mapped device buffers for the call above (one process per GPU): allocate (zero-filled), export a
+ * 64-byte CUDA IPC handle, open the handle of another rank (enables peer access), close, free. */
+int scb_peer_alloc(size_t bytes, void **dptr);
+int scb_peer_free(void *dptr);
+int scb_peer_export(void *dptr, unsigned char *handle64);
+int scb_peer_open(const unsigned char *handle64, void **dptr);
+int scb_peer_close(void *dptr);
 /* out[0] = max row sum of |entries| over the slab rows (Gershgorin bound of the local rows) */
 int scb_dense_gershgorin(int64_t N, int64_t rows, const double *slab, double *out, void *stream);
 /* G[B][b][b] = A^T Bm  for block vectors [B][N][b]  (b = 32, 64, 128) */

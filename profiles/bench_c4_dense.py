@@ -25,11 +25,13 @@ for _ in range(2): op.apply(X)
 torch.cuda.synchronize(); t=time.perf_counter()
 for _ in range(5): op.apply(X)
 torch.cuda.synchronize(); dt=(time.perf_counter()-t)/5
-if int(os.environ.get("RANK","0"))==0: print(f"world={os.environ.get('WORLD_SIZE','1')} n={n} N={3*n} slab {op.slab.numel()*8/1e9:.1f} GB assemble {t1-t0:.3f}s; apply b={b}: {dt*1e3:.2f} ms = {2*(3*n)**2*b/dt/1e12:.1f} TFLOP/s, {op.slab.numel()*8/dt/1e9:.0f} GB/s")
+if int(os.environ.get("RANK","0"))==0: print(f"world={os.environ.get('WORLD_SIZE','1')} exchange={op.exchange} n={n} N={3*n} slab {op.slab.numel()*8/1e9:.1f} GB assemble {t1-t0:.3f}s; apply b={b}: {dt*1e3:.2f} ms = {2*(3*n)**2*b/dt/1e12:.1f} TFLOP/s, {op.slab.numel()*8/dt/1e9:.0f} GB/s")
 Z = op.rigid_basis()
 torch.cuda.synchronize(); t=time.perf_counter()
 theta, A, res, iters = eig_lowest_dense(op, k, Z=Z)
 torch.cuda.synchronize(); elapsed = time.perf_counter()-t
 ub = op.spectrum_bound()   # collective: every rank calls it
+exchange = op.exchange
+op.close()                 # collective: releases the peer-mapped blocks
 if int(os.environ.get("WORLD_SIZE","1"))>1: dist.destroy_process_group()
 if int(os.environ.get("RANK","0"))==0: print(f"lowest {k} modes: {elapsed:.2f} s, {iters} outer iterations, ub={ub:.1f}, theta[0]={theta[0].item():.4g}, theta[k-1]={theta[k-1].item():.4g}, maxres={res[:k].max().item():.2e}")

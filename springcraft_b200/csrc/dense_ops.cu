@@ -2,7 +2,11 @@
 // with the Chebyshev recurrence.  This is the operator of the lowest-k solver for all-pairs force
 // fields (cutoff None: ParameterFree / Hinsen), where the Hessian is dense and
 // each GPU owns a slab of rows:   Y[rows] = alpha * (H[rows, :] X - c X[rows]) - beta W[rows].
-// The caller all-gathers the row slabs of Y over NVLink (torch.distributed / NCCL).
+// Single GPU: Y is the local slab [rows][b].  Several GPUs: the all-gather of the row slabs is FUSED
+// into the epilogue (scb_dense_slab_apply_allgather): every rank holds a full [N][b] output block in
+// peer-mapped memory (cudaIpc), and each output tile is stored straight into the full block of EVERY
+// rank over NVLink as soon as its accumulators are final, so the exchange overlaps the remaining tiles
+// of the product; a tiny barrier collective afterwards replaces the NCCL all-gather.
 //
 // DMMA (mma.sync.m8n8k4.f64) tiles of 64 rows x 64 columns, K (= N) in steps of 16, cp.async double
 // buffering.  The slab is streamed from HBM exactly once per application (8 N^2 / G bytes per GPU);
@@ -10,6 +14,8 @@
 //
 // Also exported here: the building blocks of the solver loop that the Python host code drives for
 // this path (Gram matrices, Cholesky orthonormalisation, rotation, deflation, residual norms).
+#include <string.h>
+
 #include "subspace.cuh"
 
 namespace scb {
@@ -30,11 +36,19 @@ __device__ __forceinline__ void ds_dmma(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// slab: [rows][N] row-major (rows = row1 - row0 matrix rows), X/W: [N][b], Y: [rows][b]
+constexpr int kMaxPeers = 16;
+struct PeerBlocks {
+    double* full[kMaxPeers];   // full [N][b] output block of every rank (peer-mapped), entry `rank` is local
+    int world;
+};
+
+// slab: [rows][N] row-major (rows = row1 - row0 matrix rows), X/W: [N][b].
+// PEERS == false: Y is the local slab [rows][b].  PEERS == true: rows [row0, row0+rows) of every rank's full block.
+template <bool PEERS>
 __global__ void __launch_bounds__(128)
 dense_slab_apply_kernel(int64_t N, int64_t row0, int64_t rows, int b, const double* __restrict__ slab,
                         const double* __restrict__ X, const double* __restrict__ W, double* __restrict__ Y,
-                        double alpha, double cshift, double beta, int fused) {
+                        double alpha, double cshift, double beta, int fused, PeerBlocks peers) {
     __shared__ __align__(16) double sA[2][kDsBM * kDsLDA];
     __shared__ __align__(16) double sB[2][kDsBK * kDsLDB];
     const int tid = threadIdx.x;
@@ -109,9 +123,17 @@ dense_slab_apply_kernel(int64_t N, int64_t row0, int64_t rows, int b, const doub
                 v1 = alpha * (v1 - cshift * X[g + 1]);
                 if (W && beta != 0.0) { v0 -= beta * W[g]; v1 -= beta * W[g + 1]; }
             }
-            *reinterpret_cast<double2*>(&Y[r * b + c]) = make_double2(v0, v1);
+            if (PEERS) {
+                const int64_t g = (row0 + r) * b + c;
+#pragma unroll 1
+                for (int p = 0; p < peers.world; ++p)
+                    *reinterpret_cast<double2*>(&peers.full[p][g]) = make_double2(v0, v1);
+            } else {
+                *reinterpret_cast<double2*>(&Y[r * b + c]) = make_double2(v0, v1);
+            }
         }
     }
+    if (PEERS) __threadfence_system();   // remote stores performed before the kernel retires
 }
 
 // max row sum of |entries| of a dense slab (Gershgorin bound of the local rows)
@@ -192,9 +214,67 @@ extern "C" int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const
     if (!slab || !X || !Y || N < 1 || row0 < 0 || row1 > N || row0 >= row1 || b % 64 != 0) return SCB_ERR_INVALID;
     const int64_t rows = row1 - row0;
     dim3 grid((unsigned)ceil_div(rows, kDsBM), (unsigned)(b / kDsBN));
-    dense_slab_apply_kernel<<<grid, 128, 0, as_stream(stream)>>>(N, row0, rows, b, slab, X, W, Y, alpha, cshift, beta,
-                                                              fused);
+    dense_slab_apply_kernel<false><<<grid, 128, 0, as_stream(stream)>>>(N, row0, rows, b, slab, X, W, Y, alpha, cshift,
+                                                                     beta, fused, PeerBlocks{});
     SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+extern "C" int scb_dense_slab_apply_allgather(int64_t N, int64_t row0, int64_t row1, const double* slab,
+                                              const double* X, const double* W, double* const* Y_all, int world,
+                                              int b, int fused, double alpha, double cshift, double beta,
+                                              void* stream) {
+    if (!slab || !X || !Y_all || N < 1 || row0 < 0 || row1 > N || row0 >= row1 || b % 64 != 0 || world < 1 ||
+        world > kMaxPeers)
+        return SCB_ERR_INVALID;
+    PeerBlocks peers{};
+    peers.world = world;
+    for (int p = 0; p < world; ++p) {
+        if (!Y_all[p] || Y_all[p] == X || Y_all[p] == W) return SCB_ERR_INVALID;
+        peers.full[p] = Y_all[p];
+    }
+    const int64_t rows = row1 - row0;
+    dim3 grid((unsigned)ceil_div(rows, kDsBM), (unsigned)(b / kDsBN));
+    dense_slab_apply_kernel<true><<<grid, 128, 0, as_stream(stream)>>>(N, row0, rows, b, slab, X, W, nullptr, alpha,
+                                                                    cshift, beta, fused, peers);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+// ---- peer-mapped device buffers (CUDA IPC): one process per GPU, every rank maps the buffers of the others
+extern "C" int scb_peer_alloc(size_t bytes, void** dptr) {
+    if (!dptr || bytes == 0) return SCB_ERR_INVALID;
+    SCB_CUDA(cudaMalloc(dptr, bytes));
+    SCB_CUDA(cudaMemset(*dptr, 0, bytes));
+    return SCB_OK;
+}
+
+extern "C" int scb_peer_free(void* dptr) {
+    if (!dptr) return SCB_ERR_INVALID;
+    SCB_CUDA(cudaFree(dptr));
+    return SCB_OK;
+}
+
+extern "C" int scb_peer_export(void* dptr, unsigned char* handle64) {
+    if (!dptr || !handle64) return SCB_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SCB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, sizeof(h));
+    return SCB_OK;
+}
+
+extern "C" int scb_peer_open(const unsigned char* handle64, void** dptr) {
+    if (!dptr || !handle64) return SCB_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    SCB_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SCB_OK;
+}
+
+extern "C" int scb_peer_close(void* dptr) {
+    if (!dptr) return SCB_ERR_INVALID;
+    SCB_CUDA(cudaIpcCloseMemHandle(dptr));
     return SCB_OK;
 }
 

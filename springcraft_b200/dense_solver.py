@@ -5,21 +5,25 @@ Every rank owns a slab of rows of the N x N matrix, assembled locally from the r
 coordinates (`scb_assemble_dense_allpairs`: no exchange at assembly, diagonal blocks are local row
 sums).  The eigensolver is the same Chebyshev-filtered subspace iteration as the sparse path; per
 operator application each rank computes its rows of Y = H X on the FP64 tensor cores
-(`scb_dense_slab_apply`, Chebyshev recurrence fused) and the row slabs are all-gathered with
-torch.distributed (NCCL over NVLink).  The tall-skinny steps and the small Rayleigh-Ritz problem are
+(Chebyshev recurrence fused) and the all-gather of the row slabs is fused into the SAME kernel
+(`scb_dense_slab_apply_allgather`): every rank keeps its full output blocks in peer-mapped device
+memory (`PeerBlockPool`, CUDA IPC) and the epilogue stores each finished tile into the block of every
+rank over NVLink, followed by a one-element barrier all-reduce.  ``exchange="nccl"`` keeps the plain
+`scb_dense_slab_apply` + NCCL all-gather for comparison.  The tall-skinny steps and the small Rayleigh-Ritz problem are
 replicated on every rank (they are tiny next to the slab read).  This module only orchestrates C-ABI
 kernels; the scalars of the filter live on the host (one device->host read per outer iteration).
 """
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
 from . import _engine, _lib
 from .parallel import gather_results, row_slab, world
 
-__all__ = ["DenseRowOperator", "eig_lowest_dense", "allpairs_lowest_modes"]
+__all__ = ["DenseRowOperator", "PeerBlockPool", "eig_lowest_dense", "allpairs_lowest_modes"]
 
 
 def _torch():
@@ -27,12 +31,106 @@ def _torch():
     return torch
 
 
+class _RawBlock:
+    """CUDA array interface over a raw device pointer (lets torch view a peer-mapped buffer)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerBlockPool:
+    """``count`` full [N][b] fp64 blocks per rank in peer-mapped device memory.
+
+    Every rank allocates its blocks (`scb_peer_alloc`), the 64-byte CUDA IPC handles are exchanged with
+    one all-gather, and each rank maps the blocks of all others (`scb_peer_open`).  ``table(i)`` is the
+    host array of `world` device pointers that `scb_dense_slab_apply_allgather` takes for block i.
+    Collective: construct, use and close it from every rank in the same order."""
+
+    def __init__(self, N, b, count=4):
+        torch = _torch()
+        import torch.distributed as dist
+        self.handle = _lib.require_device()
+        self.rank, self.world = world()
+        self.N, self.b, self.count = int(N), int(b), int(count)
+        nbytes = self.N * self.b * 8
+        self._local, self._opened = [], []
+        handles = torch.empty((self.count, 64), dtype=torch.uint8)
+        for i in range(self.count):
+            ptr = C.c_void_p()
+            _lib.check(self.handle.scb_peer_alloc(nbytes, C.byref(ptr)))
+            self._local.append(ptr.value)
+            buf = (C.c_ubyte * 64)()
+            _lib.check(self.handle.scb_peer_export(C.c_void_p(ptr.value), buf))
+            handles[i] = torch.tensor(list(buf), dtype=torch.uint8)
+        mine = handles.cuda()
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine)
+        self._tables, self.blocks = [], []
+        for i in range(self.count):
+            ptrs = []
+            for p in range(self.world):
+                if p == self.rank:
+                    ptrs.append(self._local[i])
+                    continue
+                raw = (C.c_ubyte * 64)(*gathered[p][i].cpu().tolist())
+                out = C.c_void_p()
+                _lib.check(self.handle.scb_peer_open(raw, C.byref(out)))
+                self._opened.append(out.value)
+                ptrs.append(out.value)
+            self._tables.append((C.c_void_p * self.world)(*ptrs))
+            self.blocks.append(torch.as_tensor(_RawBlock(self._local[i], (self.N, self.b)), device="cuda"))
+        self._token = torch.zeros(1, dtype=torch.float32, device="cuda")
+        self._next = 0
+        self._dist = dist
+        self.barrier()
+
+    def acquire(self, *busy):
+        """Index of the next block (round robin) that is none of the tensors in ``busy``."""
+        taken = {int(t.data_ptr()) for t in busy if t is not None}
+        for _ in range(self.count):
+            i = self._next
+            self._next = (self._next + 1) % self.count
+            if self._local[i] not in taken:
+                return i
+        raise RuntimeError("PeerBlockPool exhausted")
+
+    def table(self, i):
+        return self._tables[i]
+
+    def barrier(self):
+        """Stream-ordered rendezvous: returns (on the stream) once every rank has finished the kernels it
+        enqueued before its own call, i.e. all remote stores into the local blocks are complete."""
+        self._dist.all_reduce(self._token)
+
+    def close(self):
+        if not self._local:
+            return
+        torch = _torch()
+        self.blocks = []
+        torch.cuda.synchronize()
+        self.barrier()
+        torch.cuda.synchronize()
+        for ptr in self._opened:
+            _lib.check(self.handle.scb_peer_close(C.c_void_p(ptr)))
+        self.barrier()
+        torch.cuda.synchronize()
+        for ptr in self._local:
+            _lib.check(self.handle.scb_peer_free(C.c_void_p(ptr)))
+        self._local, self._opened, self._tables = [], [], []
+
+
 class DenseRowOperator:
     """Rows [row0, row1) (node units) of the dense interaction matrix of ONE structure."""
 
-    def __init__(self, coord, force_field, D=3, masses=None):
+    def __init__(self, coord, force_field, D=3, masses=None, exchange=None):
         torch = _torch()
         self.handle = _lib.require_device()
+        exchange = exchange or os.environ.get("SCB_DENSE_EXCHANGE", "peer")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
+        self._pools = {}
         coord = np.asarray(coord, dtype=np.float64)
         if coord.ndim != 2 or coord.shape[1] != 3:
             raise ValueError(f"Expected coordinates with shape (n,3), got {coord.shape}")
@@ -62,8 +160,19 @@ class DenseRowOperator:
         """Y = H X (coeffs None) or alpha (H X - c X) - beta W; returns the full [N][b] block."""
         torch = _torch()
         b = int(X.shape[1])
-        local = torch.empty(((self.row1 - self.row0) * self.D, b), dtype=torch.float64, device="cuda")
         alpha, cshift, beta = coeffs if coeffs is not None else (1.0, 0.0, 0.0)
+        if self.world > 1 and self.exchange == "peer":
+            pool = self._pools.get(b)
+            if pool is None:
+                pool = self._pools[b] = PeerBlockPool(self.N, b)
+            i = pool.acquire(X, W)
+            _lib.check(self.handle.scb_dense_slab_apply_allgather(
+                self.N, self.row0 * self.D, self.row1 * self.D, _lib.ptr(self.slab), _lib.ptr(X), _lib.ptr(W),
+                pool.table(i), self.world, b, int(coeffs is not None), float(alpha), float(cshift), float(beta),
+                _lib.stream_ptr()))
+            pool.barrier()
+            return pool.blocks[i]
+        local = torch.empty(((self.row1 - self.row0) * self.D, b), dtype=torch.float64, device="cuda")
         _lib.check(self.handle.scb_dense_slab_apply(
             self.N, self.row0 * self.D, self.row1 * self.D, _lib.ptr(self.slab), _lib.ptr(X), _lib.ptr(W),
             _lib.ptr(local), b, int(coeffs is not None), float(alpha), float(cshift), float(beta), _lib.stream_ptr()))
@@ -78,6 +187,12 @@ class DenseRowOperator:
         # ragged split: all-gather of padded slabs (node granularity keeps the slabs aligned)
         full = gather_results(local.view(self.row1 - self.row0, self.D * b), self.n, dim=0)
         return full.view(self.N, b)
+
+    def close(self):
+        """Release the peer-mapped blocks (collective; tensors returned by `apply` die with them)."""
+        for pool in self._pools.values():
+            pool.close()
+        self._pools = {}
 
     def spectrum_bound(self):
         """Gershgorin upper bound of the spectrum (max over ranks)."""
@@ -165,20 +280,23 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
     raise RuntimeError(_lib.lib().scb_status_string(_lib.SCB_ERR_NOT_CONVERGED).decode())
 
 
-def allpairs_lowest_modes(coord, force_field, k, kind="anm", masses=None, tol=3e-9):
+def allpairs_lowest_modes(coord, force_field, k, kind="anm", masses=None, tol=3e-9, exchange=None):
     """``eigen(k=...)`` for all-pairs force fields on the dense row-partitioned path: the k lowest
     modes INCLUDING the trivial ones (analytic rigid-body basis, eigenvalue 0), rows = modes.
     Call it from every rank of the process group; the result is replicated."""
     torch = _torch()
     D = 3 if kind == "anm" else 1
     ntriv = 6 if D == 3 else 1
-    op = DenseRowOperator(coord, force_field, D, masses)
+    op = DenseRowOperator(coord, force_field, D, masses, exchange=exchange)
     Z = op.rigid_basis()
     kk = max(k - ntriv, 1)
-    theta, X, _, iters = eig_lowest_dense(op, kk, Z=Z, tol=tol)
-    lam = torch.cat([torch.zeros(ntriv, dtype=torch.float64, device="cuda"), theta[:kk]])
-    modes = torch.cat([Z.T.contiguous(), X[:, :kk].T.contiguous()])
-    return lam[:k].cpu().numpy(), modes[:k].cpu().numpy(), iters
+    try:
+        theta, X, _, iters = eig_lowest_dense(op, kk, Z=Z, tol=tol)
+        lam = torch.cat([torch.zeros(ntriv, dtype=torch.float64, device="cuda"), theta[:kk]])
+        modes = torch.cat([Z.T.contiguous(), X[:, :kk].T.contiguous()])
+        return lam[:k].cpu().numpy(), modes[:k].cpu().numpy(), iters
+    finally:
+        op.close()
 
 
 del math

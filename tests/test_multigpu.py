@@ -46,6 +46,18 @@ assert np.allclose(lam4[6:56], g["eigval"][6:56], rtol=1e-8, atol=0), "C4 eigenv
 A4 = g["modes_6_106"][:50]; Q, _ = np.linalg.qr(modes4[6:56].T)
 Qa, _ = np.linalg.qr(A4.T)
 assert np.linalg.norm(Q - Qa @ (Qa.T @ Q), 2) < 1e-6, "C4 subspace"
+# the same solve with the plain NCCL all-gather instead of the fused peer-memory epilogue
+lam4n, modes4n, it4n = sc.allpairs_lowest_modes(g["coord"], sc.ParameterFreeForceField(), 56, exchange="nccl")
+assert it4n == it4 and np.allclose(lam4n, lam4, rtol=1e-11, atol=1e-12), "peer vs nccl exchange"
+# one operator application, both exchanges, bit for bit
+from springcraft_b200.dense_solver import DenseRowOperator
+Xb = torch.randn((3 * len(g["coord"]), 64), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+outs = []
+for ex in ("peer", "nccl"):
+    op = DenseRowOperator(g["coord"], sc.ParameterFreeForceField(), 3, exchange=ex)
+    outs.append(op.apply(Xb).clone()); outs.append(op.apply(Xb, Xb, (0.5, 0.1, 0.25)).clone())
+    op.close()
+assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3]), "fused all-gather differs from NCCL all-gather"
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
