@@ -189,10 +189,15 @@ int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t *rowptr, const 
  * torch.distributed all-gather of the row slabs of Y between scb_dense_slab_apply calls. ---- */
 /* Y[rows][b] = H[rows,:] X                      (fused == 0)
  *            = alpha (H[rows,:] X - c X[rows]) - beta W[rows]   (fused != 0);  rows = [row0,row1) of
- * the N x N matrix, slab = those rows (row-major, N columns); X, W are full [N][b]; b % 64 == 0. */
+ * the N x N matrix, slab = those rows (row-major, N columns); X, W are full [N][b]; b % 64 == 0.
+ * workspace (scb_dense_slab_workspace_bytes, zero-filled ONCE by the caller, reusable across calls on one
+ * stream; may be NULL): lets the launcher split K over several CTAs per output tile when the slab has too
+ * few tiles to fill the GPU (deterministic reduction: partial tiles are added in split order). */
+size_t scb_dense_slab_workspace_bytes(int64_t N, int64_t row0, int64_t row1, int b);
 int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const double *slab,
                          const double *X, const double *W, double *Y, int b, int fused,
-                         double alpha, double cshift, double beta, void *stream);
+                         double alpha, double cshift, double beta, void *workspace,
+                         size_t workspace_bytes, void *stream);
 /* Same product with the all-gather of the row slabs fused into the epilogue: Y_all is a HOST array of
  * `world` device pointers, Y_all[p] = the full [N][b] output block of rank p mapped into this process
  * (scb_peer_open; the entry of this rank is its own scb_peer_alloc buffer).  Rows [row0,row1) are stored
@@ -201,7 +206,7 @@ int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const double *sl
 int scb_dense_slab_apply_allgather(int64_t N, int64_t row0, int64_t row1, const double *slab,
                                    const double *X, const double *W, double *const *Y_all, int world,
                                    int b, int fused, double alpha, double cshift, double beta,
-                                   void *stream);
+                                   void *workspace, size_t workspace_bytes, void *stream);
 /* Peer-mapped device buffers for the call above (one process per GPU): allocate (zero-filled), export a
  * 64-byte CUDA IPC handle, open the handle of another rank (enables peer access), close, free. */
 int scb_peer_alloc(size_t bytes, void **dptr);

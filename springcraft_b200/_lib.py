@@ -85,8 +85,9 @@ SIGNATURES = {
     "scb_eig_lowest_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I64]),
     "scb_eig_lowest": (_I, [_I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _I, _I, _I, _D, _I, _I, _U64,
                             _P, _P, _P, _P, _P, _SZ, _P]),
-    "scb_dense_slab_apply": (_I, [_I64, _I64, _I64, _P, _P, _P, _P, _I, _I, _D, _D, _D, _P]),
-    "scb_dense_slab_apply_allgather": (_I, [_I64, _I64, _I64, _P, _P, _P, _P, _I, _I, _I, _D, _D, _D, _P]),
+    "scb_dense_slab_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
+    "scb_dense_slab_apply": (_I, [_I64, _I64, _I64, _P, _P, _P, _P, _I, _I, _D, _D, _D, _P, _SZ, _P]),
+    "scb_dense_slab_apply_allgather": (_I, [_I64, _I64, _I64, _P, _P, _P, _P, _I, _I, _I, _D, _D, _D, _P, _SZ, _P]),
     "scb_peer_alloc": (_I, [_SZ, _P]),
     "scb_peer_free": (_I, [_P]),
     "scb_peer_export": (_I, [_P, _P]),

@@ -14,6 +14,7 @@
 //
 // Also exported here: the building blocks of the solver loop that the Python host code drives for
 // this path (Gram matrices, Cholesky orthonormalisation, rotation, deflation, residual norms).
+#include <stdlib.h>
 #include <string.h>
 
 #include "subspace.cuh"
@@ -48,7 +49,8 @@ template <bool PEERS>
 __global__ void __launch_bounds__(128)
 dense_slab_apply_kernel(int64_t N, int64_t row0, int64_t rows, int b, const double* __restrict__ slab,
                         const double* __restrict__ X, const double* __restrict__ W, double* __restrict__ Y,
-                        double alpha, double cshift, double beta, int fused, PeerBlocks peers) {
+                        double alpha, double cshift, double beta, int fused, PeerBlocks peers, int splits,
+                        double* __restrict__ partial, unsigned int* __restrict__ counters) {
     __shared__ __align__(16) double sA[2][kDsBM * kDsLDA];
     __shared__ __align__(16) double sB[2][kDsBK * kDsLDB];
     const int tid = threadIdx.x;
@@ -82,9 +84,11 @@ dense_slab_apply_kernel(int64_t N, int64_t row0, int64_t rows, int b, const doub
         asm volatile("cp.async.commit_group;\n" ::);
     };
 
-    const int64_t nk = ceil_div(N, (int64_t)kDsBK);
-    load_stage(0, 0);
-    for (int64_t it = 0; it < nk; ++it) {
+    // split-K: blockIdx.z owns the k-steps [it0, it1) (splits == 1: all of them)
+    const int64_t nk_all = ceil_div(N, (int64_t)kDsBK);
+    const int64_t it0 = nk_all * blockIdx.z / splits, nk = nk_all * (blockIdx.z + 1) / splits;
+    load_stage((int)(it0 & 1), it0 * kDsBK);
+    for (int64_t it = it0; it < nk; ++it) {
         const int stage = (int)(it & 1);
         if (it + 1 < nk) {
             load_stage(stage ^ 1, (it + 1) * kDsBK);
@@ -109,27 +113,66 @@ dense_slab_apply_kernel(int64_t N, int64_t row0, int64_t rows, int b, const doub
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t r = m0 + wm * 32 + i * 8 + (lane >> 2);
-        if (r >= rows) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
-            double v0 = acc[i][j][0], v1 = acc[i][j][1];
-            if (fused) {
-                const int64_t g = (row0 + r) * b + c;  // global row of X / W
-                v0 = alpha * (v0 - cshift * X[g]);
-                v1 = alpha * (v1 - cshift * X[g + 1]);
-                if (W && beta != 0.0) { v0 -= beta * W[g]; v1 -= beta * W[g + 1]; }
-            }
-            if (PEERS) {
-                const int64_t g = (row0 + r) * b + c;
+    auto emit = [&](int64_t r, int c, double v0, double v1) {   // Chebyshev epilogue + store of two columns
+        if (fused) {
+            const int64_t g = (row0 + r) * b + c;  // global row of X / W
+            v0 = alpha * (v0 - cshift * X[g]);
+            v1 = alpha * (v1 - cshift * X[g + 1]);
+            if (W && beta != 0.0) { v0 -= beta * W[g]; v1 -= beta * W[g + 1]; }
+        }
+        if (PEERS) {
+            const int64_t g = (row0 + r) * b + c;
 #pragma unroll 1
-                for (int p = 0; p < peers.world; ++p)
-                    *reinterpret_cast<double2*>(&peers.full[p][g]) = make_double2(v0, v1);
-            } else {
-                *reinterpret_cast<double2*>(&Y[r * b + c]) = make_double2(v0, v1);
+            for (int p = 0; p < peers.world; ++p)
+                *reinterpret_cast<double2*>(&peers.full[p][g]) = make_double2(v0, v1);
+        } else {
+            *reinterpret_cast<double2*>(&Y[r * b + c]) = make_double2(v0, v1);
+        }
+    };
+    if (splits == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = m0 + wm * 32 + i * 8 + (lane >> 2);
+            if (r >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                emit(r, n0 + wn * 32 + j * 8 + 2 * (lane & 3), acc[i][j][0], acc[i][j][1]);
+        }
+    } else {
+        // deterministic split-K: every split parks its 64x64 partial tile; the CTA that arrives last adds the
+        // partials in split order (the same order whichever CTA is last) and runs the epilogue
+        __shared__ int is_last;
+        const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        const int64_t ntiles = (int64_t)gridDim.x * gridDim.y;
+        double* mine = partial + ((int64_t)blockIdx.z * ntiles + tile) * (kDsBM * kDsBN);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int lr = wm * 32 + i * 8 + (lane >> 2), lc = wn * 32 + j * 8 + 2 * (lane & 3);
+                *reinterpret_cast<double2*>(&mine[lr * kDsBN + lc]) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int seen = atomicAdd(&counters[tile], 1u);
+            is_last = (seen == (unsigned int)splits - 1);
+            if (is_last) counters[tile] = 0;   // ready for the next launch
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const double* base = partial + tile * (kDsBM * kDsBN);
+            for (int q = tid; q < kDsBM * kDsBN / 2; q += 128) {
+                const int lr = q / (kDsBN / 2), lc = 2 * (q % (kDsBN / 2));
+                double v0 = 0.0, v1 = 0.0;
+                for (int sp = 0; sp < splits; ++sp) {
+                    const double2 t = *reinterpret_cast<const double2*>(&base[(int64_t)sp * ntiles * (kDsBM * kDsBN) + lr * kDsBN + lc]);
+                    v0 += t.x;
+                    v1 += t.y;
+                }
+                const int64_t r = m0 + lr;
+                if (r < rows) emit(r, n0 + lc, v0, v1);
             }
         }
     }
@@ -208,22 +251,61 @@ __global__ void transpose_small_kernel(int b, const double* __restrict__ in, dou
 
 using namespace scb;
 
-extern "C" int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const double* slab, const double* X,
-                                    const double* W, double* Y, int b, int fused, double alpha, double cshift,
-                                    double beta, void* stream) {
-    if (!slab || !X || !Y || N < 1 || row0 < 0 || row1 > N || row0 >= row1 || b % 64 != 0) return SCB_ERR_INVALID;
-    const int64_t rows = row1 - row0;
-    dim3 grid((unsigned)ceil_div(rows, kDsBM), (unsigned)(b / kDsBN));
-    dense_slab_apply_kernel<false><<<grid, 128, 0, as_stream(stream)>>>(N, row0, rows, b, slab, X, W, Y, alpha, cshift,
-                                                                     beta, fused, PeerBlocks{});
+// Split-K factor: a slab with few 64x64 output tiles (many GPUs, or a small matrix) would leave SMs with
+// uneven tile counts; cut K until there are >= 12 work units per SM, i.e. 3 waves of the 4 resident CTAs
+// (measured: 7,500 x 60,000 slab 4.51 -> 3.63 ms, 15,000 rows 9.06 -> 7.2 ms; the reduction is deterministic).
+static int slab_splits(int64_t N, int64_t rows, int b) {
+    const int64_t tiles = ceil_div(rows, (int64_t)kDsBM) * (b / kDsBN);
+    int splits = 1;
+    if (const char* env = getenv("SCB_SLAB_SPLITS")) return atoi(env) > 0 ? atoi(env) : 1;
+    while (tiles * splits < 12 * kNumSM && splits < 8 && N / (2 * splits) >= 64 * kDsBK) splits *= 2;
+    return splits;
+}
+
+static size_t slab_partial_bytes(int64_t rows, int b, int splits) {
+    const int64_t tiles = ceil_div(rows, (int64_t)kDsBM) * (b / kDsBN);
+    return (size_t)256 + sizeof(double) * (size_t)splits * tiles * kDsBM * kDsBN + 256 + sizeof(unsigned int) * tiles;
+}
+
+extern "C" size_t scb_dense_slab_workspace_bytes(int64_t N, int64_t row0, int64_t row1, int b) {
+    if (N < 1 || row1 <= row0 || b % 64 != 0) return 0;
+    return slab_partial_bytes(row1 - row0, b, 8);   // enough for any split factor the launcher may pick
+}
+
+template <bool PEERS>
+static int slab_launch(int64_t N, int64_t row0, int64_t rows, int b, const double* slab, const double* X,
+                       const double* W, double* Y, double alpha, double cshift, double beta, int fused,
+                       const PeerBlocks& peers, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    int splits = workspace ? slab_splits(N, rows, b) : 1;
+    while (splits > 1 && slab_partial_bytes(rows, b, splits) > workspace_bytes) splits /= 2;
+    const int64_t tiles = ceil_div(rows, (int64_t)kDsBM) * (b / kDsBN);
+    double* partial = nullptr;
+    unsigned int* counters = nullptr;
+    if (splits > 1) {
+        Arena ar(workspace, workspace_bytes);
+        partial = ar.take<double>((size_t)splits * tiles * kDsBM * kDsBN);
+        counters = ar.take<unsigned int>((size_t)tiles);
+        if (!ar.ok()) return SCB_ERR_WORKSPACE;
+    }
+    dim3 grid((unsigned)ceil_div(rows, kDsBM), (unsigned)(b / kDsBN), (unsigned)splits);
+    dense_slab_apply_kernel<PEERS><<<grid, 128, 0, st>>>(N, row0, rows, b, slab, X, W, Y, alpha, cshift, beta, fused,
+                                                         peers, splits, partial, counters);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
+}
+
+extern "C" int scb_dense_slab_apply(int64_t N, int64_t row0, int64_t row1, const double* slab, const double* X,
+                                    const double* W, double* Y, int b, int fused, double alpha, double cshift,
+                                    double beta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!slab || !X || !Y || N < 1 || row0 < 0 || row1 > N || row0 >= row1 || b % 64 != 0) return SCB_ERR_INVALID;
+    return slab_launch<false>(N, row0, row1 - row0, b, slab, X, W, Y, alpha, cshift, beta, fused, PeerBlocks{},
+                              workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int scb_dense_slab_apply_allgather(int64_t N, int64_t row0, int64_t row1, const double* slab,
                                               const double* X, const double* W, double* const* Y_all, int world,
                                               int b, int fused, double alpha, double cshift, double beta,
-                                              void* stream) {
+                                              void* workspace, size_t workspace_bytes, void* stream) {
     if (!slab || !X || !Y_all || N < 1 || row0 < 0 || row1 > N || row0 >= row1 || b % 64 != 0 || world < 1 ||
         world > kMaxPeers)
         return SCB_ERR_INVALID;
@@ -233,12 +315,8 @@ extern "C" int scb_dense_slab_apply_allgather(int64_t N, int64_t row0, int64_t r
         if (!Y_all[p] || Y_all[p] == X || Y_all[p] == W) return SCB_ERR_INVALID;
         peers.full[p] = Y_all[p];
     }
-    const int64_t rows = row1 - row0;
-    dim3 grid((unsigned)ceil_div(rows, kDsBM), (unsigned)(b / kDsBN));
-    dense_slab_apply_kernel<true><<<grid, 128, 0, as_stream(stream)>>>(N, row0, rows, b, slab, X, W, nullptr, alpha,
-                                                                    cshift, beta, fused, peers);
-    SCB_LAUNCH_CHECK();
-    return SCB_OK;
+    return slab_launch<true>(N, row0, row1 - row0, b, slab, X, W, nullptr, alpha, cshift, beta, fused, peers, workspace,
+                             workspace_bytes, as_stream(stream));
 }
 
 // ---- peer-mapped device buffers (CUDA IPC): one process per GPU, every rank maps the buffers of the others

@@ -131,6 +131,7 @@ class DenseRowOperator:
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.exchange = exchange
         self._pools = {}
+        self._workspaces = {}
         coord = np.asarray(coord, dtype=np.float64)
         if coord.ndim != 2 or coord.shape[1] != 3:
             raise ValueError(f"Expected coordinates with shape (n,3), got {coord.shape}")
@@ -161,6 +162,10 @@ class DenseRowOperator:
         torch = _torch()
         b = int(X.shape[1])
         alpha, cshift, beta = coeffs if coeffs is not None else (1.0, 0.0, 0.0)
+        ws = self._workspaces.get(b)
+        if ws is None:   # split-K scratch (zeroed once: the tile counters return to 0 after every launch)
+            nbytes = self.handle.scb_dense_slab_workspace_bytes(self.N, self.row0 * self.D, self.row1 * self.D, b)
+            ws = self._workspaces[b] = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
         if self.world > 1 and self.exchange == "peer":
             pool = self._pools.get(b)
             if pool is None:
@@ -169,13 +174,14 @@ class DenseRowOperator:
             _lib.check(self.handle.scb_dense_slab_apply_allgather(
                 self.N, self.row0 * self.D, self.row1 * self.D, _lib.ptr(self.slab), _lib.ptr(X), _lib.ptr(W),
                 pool.table(i), self.world, b, int(coeffs is not None), float(alpha), float(cshift), float(beta),
-                _lib.stream_ptr()))
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
             pool.barrier()
             return pool.blocks[i]
         local = torch.empty(((self.row1 - self.row0) * self.D, b), dtype=torch.float64, device="cuda")
         _lib.check(self.handle.scb_dense_slab_apply(
             self.N, self.row0 * self.D, self.row1 * self.D, _lib.ptr(self.slab), _lib.ptr(X), _lib.ptr(W),
-            _lib.ptr(local), b, int(coeffs is not None), float(alpha), float(cshift), float(beta), _lib.stream_ptr()))
+            _lib.ptr(local), b, int(coeffs is not None), float(alpha), float(cshift), float(beta),
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         if self.world == 1:
             return local
         if self.n % self.world == 0:
