@@ -31,6 +31,12 @@ __device__ __forceinline__ void ds_cp_async16(void* smem, const void* gmem, bool
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
 }
 
+__device__ __forceinline__ void ds_cp_async8(void* smem, const void* gmem, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
 __device__ __forceinline__ void ds_dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
@@ -64,14 +70,23 @@ dense_slab_apply_kernel(int64_t N, int64_t row0, int64_t rows, int b, const doub
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    const bool even_n = (N & 1) == 0;
     auto load_stage = [&](int stage, int64_t kk) {
         // A: 64 rows x 16 doubles = 512 16-byte chunks (4 per thread)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = tid + q * 128;
             const int r = c >> 3, kc = (c & 7) * 2;
-            const bool ok = (m0 + r) < rows && (kk + kc) < N;
-            ds_cp_async16(&sA[stage][r * kDsLDA + kc], ok ? (const void*)(slab + (m0 + r) * N + kk + kc) : (const void*)slab, ok);
+            if (even_n) {
+                const bool ok = (m0 + r) < rows && (kk + kc) < N;
+                ds_cp_async16(&sA[stage][r * kDsLDA + kc], ok ? (const void*)(slab + (m0 + r) * N + kk + kc) : (const void*)slab, ok);
+            } else {   // odd N: rows of the slab are only 8-byte aligned
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool ok = (m0 + r) < rows && (kk + kc + e) < N;
+                    ds_cp_async8(&sA[stage][r * kDsLDA + kc + e], ok ? (const void*)(slab + (m0 + r) * N + kk + kc + e) : (const void*)slab, ok);
+                }
+            }
         }
         // B: 16 rows (k) x 64 doubles = 512 chunks (4 per thread)
 #pragma unroll

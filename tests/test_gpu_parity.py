@@ -476,6 +476,32 @@ def test_c4_dense_row_operator(k):
     assert np.abs(H @ modes[:6].T).max() <= 1e-10 * np.abs(H).max()
 
 
+@pytest.mark.parametrize("splits", [1, 2, 4, 8])
+def test_dense_slab_split_k(splits, monkeypatch):
+    """Split-K variant of the slab product (used when a rank's slab has too few tiles to fill the GPU): same
+    result as torch's fp64 matmul, fused Chebyshev epilogue included, ragged row/column counts, and
+    bit-reproducible from call to call (deterministic reduction order)."""
+    import torch
+    from springcraft_b200 import _lib
+    monkeypatch.setenv("SCB_SLAB_SPLITS", str(splits))
+    h = _lib.require_device()
+    rows, N, b, row0 = 1000, 5003, 128, 37
+    g = torch.Generator("cuda").manual_seed(3)
+    slab = torch.randn((rows, N), dtype=torch.float64, device="cuda", generator=g)
+    X = torch.randn((N, b), dtype=torch.float64, device="cuda", generator=g)
+    W = torch.randn((N, b), dtype=torch.float64, device="cuda", generator=g)
+    ws = torch.zeros(h.scb_dense_slab_workspace_bytes(N, row0, row0 + rows, b), dtype=torch.uint8, device="cuda")
+    outs = []
+    for _ in range(2):
+        Y = torch.empty((rows, b), dtype=torch.float64, device="cuda")
+        _lib.check(h.scb_dense_slab_apply(N, row0, row0 + rows, _lib.ptr(slab), _lib.ptr(X), _lib.ptr(W), _lib.ptr(Y),
+                                          b, 1, 0.7, 0.3, 0.2, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        outs.append(Y)
+    ref = 0.7 * (slab @ X - 0.3 * X[row0:row0 + rows]) - 0.2 * W[row0:row0 + rows]
+    assert float((outs[0] - ref).abs().max() / ref.abs().max()) <= 1e-13
+    assert torch.equal(outs[0], outs[1])
+
+
 # --------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("key", ["invariant13", "hinsen", "e_anm", "sd_enm", "pfree"])
 def test_1l2y_nma_products(structures, key):
