@@ -14,6 +14,9 @@
 // steps only the pairs ACROSS the two blocks, i.e. each index pair is rotated
 // once per sweep (cyclic-by-blocks ordering).
 // Sweeps repeat until the off-diagonal Frobenius norm is ~1e-14 of the total.
+// A batch is solved in groups of up to 32 matrices that share every launch
+// (grid.y = matrix): the pivots of one N=900 matrix occupy only 15 SMs, so
+// batching is what fills the GPU for ensembles of small structures.
 #include <stdlib.h>
 
 #include "subspace.cuh"
@@ -49,6 +52,9 @@ __global__ void bj_init_kernel(int N, int Np, const double* __restrict__ A, doub
                                double* __restrict__ V) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (int64_t)Np * Np) return;
+    A += (int64_t)blockIdx.y * N * N;
+    Ap += (int64_t)blockIdx.y * Np * Np;
+    V += (int64_t)blockIdx.y * Np * Np;
     const int i = (int)(q / Np), j = (int)(q % Np);
     double v = 0.0;
     if (i < N && j < N) v = (j <= i) ? A[(int64_t)i * N + j] : A[(int64_t)j * N + i];
@@ -61,9 +67,13 @@ constexpr int kPivotThreads = 512;
 
 __global__ void __launch_bounds__(kPivotThreads)
 bj_pivot_kernel(int Np, int nb, int step, const double* __restrict__ Ap, double* __restrict__ R,
-                int32_t* __restrict__ active, int inner_sweeps, int cross_only) {
+                int32_t* __restrict__ active, int inner_sweeps, int cross_only, const int32_t* __restrict__ mdone) {
     constexpr int LD = kPW + 1;
     constexpr int NT = kPivotThreads;
+    if (mdone[blockIdx.y]) return;   // this matrix of the group has converged
+    Ap += (int64_t)blockIdx.y * Np * Np;
+    R += (int64_t)blockIdx.y * (nb / 2) * 2 * kPW * kPW;
+    active += (int64_t)blockIdx.y * (nb / 2);
     extern __shared__ double sm[];
     double* S = sm;
     double* V = S + kPW * LD;
@@ -144,8 +154,13 @@ __device__ __forceinline__ int pair_index(int I, int J, int r) { return r < kBW 
 // CTAs [nA, nA + (Np/64) * npairs): V[64 rows][columns of pair l] <- (same) R_l.
 __global__ void __launch_bounds__(256)
 bj_update_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __restrict__ V,
-                 const double* __restrict__ R, const int32_t* __restrict__ active) {
+                 const double* __restrict__ R, const int32_t* __restrict__ active, const int32_t* __restrict__ mdone) {
     constexpr int TLD = kPW + 1;   // transposition buffer: odd leading dimension
+    if (mdone[blockIdx.y]) return;
+    Ap += (int64_t)blockIdx.y * Np * Np;
+    V += (int64_t)blockIdx.y * Np * Np;
+    R += (int64_t)blockIdx.y * (nb / 2) * 2 * kPW * kPW;
+    active += (int64_t)blockIdx.y * (nb / 2);
     extern __shared__ double sm[];
     double* sL = sm;                    // left factor (R_k^T, then the mirror staging buffer)
     double* sM = sm + kPW * kTLD;       // the tile (then T = R_k^T A_kl)
@@ -236,8 +251,12 @@ bj_update_kernel(int Np, int nb, int step, double* __restrict__ Ap, double* __re
 
 // norms[0] += sum of squared off-diagonal entries, norms[1] += squared diagonal
 __global__ void __launch_bounds__(256)
-bj_norms_kernel(int Np, const double* __restrict__ Ap, double* __restrict__ norms) {
+bj_norms_kernel(int Np, const double* __restrict__ Ap, double* __restrict__ norms,
+                const int32_t* __restrict__ mdone) {
     __shared__ double red[8];
+    if (mdone[blockIdx.y]) return;
+    Ap += (int64_t)blockIdx.y * Np * Np;
+    norms += 2 * blockIdx.y;
     double off = 0.0, dg = 0.0;
     const int64_t total = (int64_t)Np * Np;
     for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
@@ -255,6 +274,9 @@ bj_rank_kernel(int N, int Np, const double* __restrict__ Ap, int32_t* __restrict
                double* __restrict__ eigval) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    Ap += (int64_t)blockIdx.y * Np * Np;
+    rank += (int64_t)blockIdx.y * N;
+    eigval += (int64_t)blockIdx.y * N;
     const double v = Ap[(int64_t)i * Np + i];
     int r = 0;
     for (int k = 0; k < N; ++k) {
@@ -272,6 +294,9 @@ bj_export_kernel(int N, int Np, const double* __restrict__ V, const int32_t* __r
     __shared__ double tile[32][33];
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    V += (int64_t)blockIdx.z * Np * Np;
+    rank += (int64_t)blockIdx.z * N;
+    modes += (int64_t)blockIdx.z * N * N;
     for (int rr = ty; rr < 32; rr += 8) {
         const int r = r0 + rr, c = c0 + tx;
         tile[rr][tx] = (r < N && c < N) ? V[(int64_t)r * Np + c] : 0.0;
@@ -290,35 +315,60 @@ static int padded_order(int N) {
     return nb * kBW;
 }
 
+// mdone[g] = 1 once the off-diagonal norm of matrix g is negligible (or g is beyond the group)
+__global__ void bj_flag_kernel(int G, int live, const double* __restrict__ norms, int32_t* __restrict__ mdone) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    if (g >= live) { mdone[g] = 1; return; }
+    if (mdone[g]) return;
+    const double off = norms[2 * g], dg = norms[2 * g + 1];
+    mdone[g] = (off <= 1e-28 * (off + dg)) ? 1 : 0;
+}
+
 struct BjWork {
     double *Ap, *V, *R, *norms;
-    int32_t *active, *rank;
+    int32_t *active, *rank, *mdone;
 };
 
-static void bj_carve(Arena& ar, BjWork* w, int N) {
+static size_t bj_bytes_per_matrix(int N) {
+    const size_t Np = (size_t)padded_order(N);
+    const size_t nb = Np / kBW;
+    return sizeof(double) * (2 * Np * Np + (nb / 2) * 2 * kPW * kPW + 2) + sizeof(int32_t) * (nb / 2 + (size_t)N + 1);
+}
+
+// matrices of a batch that share the launches: as many as fit ~2 GB of workspace, at most 32
+static int bj_group(int B, int N) {
+    size_t g = ((size_t)2 << 30) / bj_bytes_per_matrix(N);
+    if (g < 1) g = 1;
+    if (g > 32) g = 32;
+    return (int)(g < (size_t)B ? g : (size_t)B);
+}
+
+static void bj_carve(Arena& ar, BjWork* w, int N, int G) {
     const int Np = padded_order(N);
     const int nb = Np / kBW;
-    w->Ap = ar.take<double>((size_t)Np * Np);
-    w->V = ar.take<double>((size_t)Np * Np);
-    w->R = ar.take<double>((size_t)(nb / 2) * 2 * kPW * kPW);
-    w->norms = ar.take<double>(2);
-    w->active = ar.take<int32_t>(nb / 2);
-    w->rank = ar.take<int32_t>(N);
+    w->Ap = ar.take<double>((size_t)G * Np * Np);
+    w->V = ar.take<double>((size_t)G * Np * Np);
+    w->R = ar.take<double>((size_t)G * (nb / 2) * 2 * kPW * kPW);
+    w->norms = ar.take<double>((size_t)2 * G);
+    w->active = ar.take<int32_t>((size_t)G * (nb / 2));
+    w->rank = ar.take<int32_t>((size_t)G * N);
+    w->mdone = ar.take<int32_t>((size_t)G);
 }
 
 size_t eig_full_block_workspace_bytes(int B, int N) {
-    (void)B;  // matrices of a batch are processed one after the other
     Arena ar(nullptr, 0);
     BjWork w;
-    bj_carve(ar, &w, N);
+    bj_carve(ar, &w, N, bj_group(B, N));
     return ar.off + 256;
 }
 
 int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void* workspace, size_t workspace_bytes,
                    cudaStream_t st) {
+    const int G = bj_group(B, N);
     Arena ar(workspace, workspace_bytes);
     BjWork w;
-    bj_carve(ar, &w, N);
+    bj_carve(ar, &w, N, G);
     if (!ar.ok()) return SCB_ERR_WORKSPACE;
     const int Np = padded_order(N);
     const int nb = Np / kBW;
@@ -335,44 +385,50 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
     if (const char* env = getenv("SCB_BJ_INNER")) inner_sweeps = atoi(env) > 0 ? atoi(env) : inner_sweeps;
     int cross = 1;
     if (const char* env = getenv("SCB_BJ_CROSS")) cross = atoi(env);
-    double* h_norms = nullptr;
-    SCB_CUDA(cudaMallocHost(&h_norms, 2 * sizeof(double)));
+    int32_t* h_done = nullptr;
+    SCB_CUDA(cudaMallocHost(&h_done, G * sizeof(int32_t)));
     int status = SCB_OK;
-    for (int s = 0; s < B && status == SCB_OK; ++s) {
-        const double* As = A + (int64_t)s * N * N;
-        bj_init_kernel<<<(unsigned)ceil_div((int64_t)Np * Np, 256), 256, 0, st>>>(N, Np, As, w.Ap, w.V);
+    for (int s0 = 0; s0 < B && status == SCB_OK; s0 += G) {
+        const int live = (B - s0 < G) ? B - s0 : G;   // matrices in this group
+        bj_init_kernel<<<dim3((unsigned)ceil_div((int64_t)Np * Np, 256), (unsigned)live), 256, 0, st>>>(
+            N, Np, A + (int64_t)s0 * N * N, w.Ap, w.V);
+        SCB_CUDA(cudaMemsetAsync(w.mdone, 0, G * sizeof(int32_t), st));
         count_launches(3);  // init + rank + export
         bool converged = false;
         for (int sweep = 0; sweep < 60 && !converged; ++sweep) {
             for (int step = 0; step < nb - 1; ++step) {
                 // step 0 of a sweep rotates every pair inside its 64x64 pivots (this covers the pairs inside each
                 // diagonal block once per sweep); the other steps only rotate pairs ACROSS the two blocks
-                bj_pivot_kernel<<<npairs, kPivotThreads, smem_pivot, st>>>(Np, nb, step, w.Ap, w.R, w.active, inner_sweeps,
-                                                                 (cross && step > 0) ? 1 : 0);
-                bj_update_kernel<<<npairs * (npairs + 1) / 2 + (Np / kPW) * npairs, 256, smem_tile, st>>>(
-                    Np, nb, step, w.Ap, w.V, w.R, w.active);
+                bj_pivot_kernel<<<dim3(npairs, live), kPivotThreads, smem_pivot, st>>>(
+                    Np, nb, step, w.Ap, w.R, w.active, inner_sweeps, (cross && step > 0) ? 1 : 0, w.mdone);
+                bj_update_kernel<<<dim3(npairs * (npairs + 1) / 2 + (Np / kPW) * npairs, live), 256, smem_tile, st>>>(
+                    Np, nb, step, w.Ap, w.V, w.R, w.active, w.mdone);
                 count_launches(2);
             }
-            cudaMemsetAsync(w.norms, 0, 2 * sizeof(double), st);
-            bj_norms_kernel<<<4 * kNumSM, 256, 0, st>>>(Np, w.Ap, w.norms);
-            count_launches(1);
-            if (cudaMemcpyAsync(h_norms, w.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemsetAsync(w.norms, 0, 2 * G * sizeof(double), st);
+            const int norm_ctas = (4 * kNumSM + live - 1) / live;
+            bj_norms_kernel<<<dim3(norm_ctas, live), 256, 0, st>>>(Np, w.Ap, w.norms, w.mdone);
+            bj_flag_kernel<<<1, 32, 0, st>>>(G, live, w.norms, w.mdone);
+            count_launches(2);
+            if (cudaMemcpyAsync(h_done, w.mdone, G * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaStreamSynchronize(st) != cudaSuccess) {
                 set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
                 status = SCB_ERR_CUDA;
                 break;
             }
-            if (h_norms[0] <= 1e-28 * (h_norms[0] + h_norms[1])) converged = true;
+            converged = true;
+            for (int g = 0; g < live; ++g) converged = converged && h_done[g] != 0;
         }
         if (status != SCB_OK) break;
         if (!converged) { status = SCB_ERR_NOT_CONVERGED; break; }
-        bj_rank_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, Np, w.Ap, w.rank, eigval + (int64_t)s * N);
-        bj_export_kernel<<<dim3((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 32)), 256, 0, st>>>(
-            N, Np, w.V, w.rank, modes + (int64_t)s * N * N);
+        bj_rank_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)live), 256, 0, st>>>(N, Np, w.Ap, w.rank,
+                                                                                         eigval + (int64_t)s0 * N);
+        bj_export_kernel<<<dim3((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 32), (unsigned)live), 256, 0, st>>>(
+            N, Np, w.V, w.rank, modes + (int64_t)s0 * N * N);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); status = SCB_ERR_CUDA; }
     }
-    cudaFreeHost(h_norms);
+    cudaFreeHost(h_done);
     return status;
 }
 

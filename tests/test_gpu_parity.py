@@ -271,6 +271,34 @@ def test_eig_full_block_random(N):
     assert np.abs(A @ modes.T - modes.T * lam).max() <= 1e-11 * scale
 
 
+def test_eig_full_block_batched():
+    """A batch of matrices shares every launch of the block-Jacobi solver (grid.y = matrix): matrices that
+    converge after different numbers of sweeps (random, rank-deficient, already diagonal, tightly clustered)
+    must each match LAPACK."""
+    import torch
+    from springcraft_b200 import _engine
+    N = 130
+    rng = np.random.default_rng(5)
+    mats = []
+    for kind in range(5):
+        A = rng.normal(size=(N, N)); A = A + A.T
+        if kind == 1:
+            G = rng.normal(size=(N, N - 11)); A = G @ G.T
+        elif kind == 2:
+            A = np.diag(rng.normal(size=N))
+        elif kind == 3:
+            A = np.eye(N) + 1e-6 * A
+        mats.append(A)
+    lam, modes = _engine.eig_full_dense(torch.from_numpy(np.stack(mats)).cuda())
+    lam, modes = lam.cpu().numpy(), modes.cpu().numpy()
+    for A, l, m in zip(mats, lam, modes):
+        want = np.linalg.eigvalsh(A)
+        scale = np.abs(want).max()
+        assert np.allclose(l, want, rtol=0, atol=1e-12 * scale)
+        assert np.allclose(m @ m.T, np.eye(N), atol=1e-12)
+        assert np.abs(A @ m.T - m.T * l).max() <= 1e-11 * scale
+
+
 @pytest.mark.parametrize("key", ["e_anm", "sd_enm"])
 @pytest.mark.parametrize("c", [0, 1, 2, 4095])
 def test_c3_lowest_modes(key, c):
