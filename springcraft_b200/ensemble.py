@@ -33,7 +33,11 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
     Returns the k lowest NON-trivial modes' eigenvalues (reference indices
     6..6+k-1 for ANM, 1..k for GNM) and ``mean_square_fluctuation(mode_subset=
     those modes)`` for every conformation.  Host->device and device->host copies
-    happen inside the single C-ABI call ``scb_enm_ensemble_host``."""
+    happen inside the single C-ABI call ``scb_enm_ensemble_host``.
+
+    ``k=None`` asks for ALL non-trivial modes (the reference's default mode set,
+    nma.py:145-151): dense matrices go through the batched full-spectrum solver
+    in chunks; two orders of magnitude slower than a small k."""
     import torch
     handle = _lib.require_device()
     coords = np.ascontiguousarray(coords, dtype=np.float64)
@@ -41,6 +45,8 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
         raise ValueError(f"Expected coordinates with shape (B,n,3), got {coords.shape}")
     B, n = int(coords.shape[0]), int(coords.shape[1])
     D = 3 if kind == "anm" else 1
+    if k is None:
+        return _ensemble_all_modes(coords, force_field, D, masses, return_modes)
     if force_field.natoms is not None and force_field.natoms != n:
         raise ValueError(f"Got coordinates for {n} atoms, but forcefield was built for {force_field.natoms} atoms")
     built = force_field._descriptor(n)
@@ -63,6 +69,33 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
     _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
     del keep
     return EnsembleResult(eig, msf, modes, int(npairs.value), status == 0)
+
+
+def _ensemble_all_modes(coords, force_field, D, masses, return_modes):
+    """All non-trivial modes per conformation: batched assembly -> dense -> block-Jacobi groups -> MSF."""
+    from . import _engine
+    B, n = int(coords.shape[0]), int(coords.shape[1])
+    N = D * n
+    ntriv = 6 if D == 3 else 1
+    if N <= ntriv:
+        raise ValueError("system too small: no non-trivial modes")
+    chunk = int(max(1, min(64, 2e9 // (40 * N * N))))
+    eig = np.empty((B, N - ntriv))
+    msf = np.empty((B, n))
+    modes_out = np.empty((B, N - ntriv, N)) if return_modes else None
+    npairs = 0
+    for c0 in range(0, B, chunk):
+        c1 = min(B, c0 + chunk)
+        model = _engine.DeviceModel(coords[c0:c1], force_field, D, masses)
+        lam, modes = _engine.eig_full_dense(model.dense())
+        npairs += int(model.P)
+        lam_nt = lam[:, ntriv:].contiguous()
+        modes_nt = modes[:, ntriv:, :].contiguous()
+        eig[c0:c1] = lam_nt.cpu().numpy()
+        msf[c0:c1] = _engine.modes_msf(D, lam_nt, modes_nt).cpu().numpy()
+        if return_modes:
+            modes_out[c0:c1] = modes_nt.cpu().numpy()
+    return EnsembleResult(eig, msf, modes_out, npairs, True)
 
 
 def enm_ensemble_device(xyz_soa, force_field, k=20, kind="anm", masses=None, tol=3e-9, out=None):

@@ -417,6 +417,33 @@ def test_ensemble_variants_vs_oracle():
             assert np.allclose(res.msf[q], want, rtol=PROD_RTOL, atol=0)
 
 
+def test_ensemble_all_modes_vs_oracle():
+    """``enm_ensemble(k=None)``: every non-trivial mode per conformation through the batched full-spectrum
+    solver (the reference's default mode set for MSF, nma.py:145-151), ANM with masses and GNM."""
+    n = 100
+    base = orc.synthetic_chain(n, seed=4)
+    res_name, chain_id, res_id = orc.synthetic_sequence(n, seed=4)
+    rng = np.random.default_rng(4)
+    coords = base[None] + rng.normal(0, 0.3, size=(5, n, 3))
+    masses = rng.uniform(60, 190, n)
+    atoms = sc.AtomArray(base, res_name, chain_id, res_id)
+    spec = orc.preset_spec("e_anm", res_name, chain_id, res_id)
+    res = sc.enm_ensemble(coords, sc.TabulatedForceField.e_anm(atoms), k=None, masses=masses, return_modes=True)
+    assert res.eigenvalues.shape == (5, 3 * n - 6) and res.msf.shape == (5, n)
+    for q in range(len(coords)):
+        H, _ = orc.compute_hessian(coords[q], spec, masses=masses)
+        lam, vec = np.linalg.eigh(H)
+        assert np.allclose(res.eigenvalues[q], lam[6:], rtol=EIG_RTOL, atol=1e-10 * lam[-1])
+        assert np.allclose(res.msf[q], orc.mean_square_fluctuation(lam, vec.T, 3), rtol=PROD_RTOL, atol=0)
+        assert np.abs(H @ res.modes[q].T - res.modes[q].T * res.eigenvalues[q]).max() <= 1e-10 * lam[-1]
+    gres = sc.enm_ensemble(coords, sc.InvariantForceField(10.0), k=None, kind="gnm")
+    for q in range(len(coords)):
+        K, _ = orc.compute_kirchhoff(coords[q], orc.FFSpec("invariant", 10.0))
+        lam, vec = np.linalg.eigh(K)
+        assert np.allclose(gres.eigenvalues[q], lam[1:], rtol=EIG_RTOL, atol=1e-10 * lam[-1])
+        assert np.allclose(gres.msf[q], orc.mean_square_fluctuation(lam, vec.T, 1), rtol=PROD_RTOL, atol=0)
+
+
 def test_degenerate_inputs():
     """No contacts at all, and structures of 2-3 nodes (edge cases of the contact / assembly kernels)."""
     rng = np.random.default_rng(1)
