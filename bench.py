@@ -340,7 +340,7 @@ def run_gpu(args):
                                    "dense Hessian + full np.linalg.eigh + MSF (reference algorithm)"},
         "single_structure_20k": large,
         "solver": {"outer_iterations_mean": float(iters_d.abs().double().mean().item()),
-                   "outer_iterations_max": int(iters_d.abs().max().item()), "filter_degree": 24,
+                   "outer_iterations_max": int(iters_d.abs().max().item()), "filter_degree": int(os.environ.get("SCB_DEGREE", 32)),
                    "block": 32, "ordered_pairs": int(n_pairs)},
     }
     print(json.dumps(line))

@@ -508,6 +508,19 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
         const int d = (int)ceil(need / log_rho) + 1;
         next_degree = min(degree, max(8, d));
     }
+    // Conditioning guard: a degree-m filter amplifies the lowest Ritz direction by T_m(x0), x0 = (c - a0) / half,
+    // against the direction at `lo`.  When the block spans a large part of the spectrum (small systems) that
+    // ratio exceeds 1/eps and the filtered block loses rank; keep it below ~1e9 (no effect on protein-sized
+    // systems, where x0 - 1 is a few percent and the cap is > 50).
+    if (!finished && e.iters >= 2) {
+        const double half = 0.5 * (e.ub - lo), c = 0.5 * (e.ub + lo);
+        const double x0 = (c - e.a0) / half;
+        if (x0 > 1.0) {
+            const double growth = log(x0 + sqrt(x0 * x0 - 1.0));   // acosh(x0); T_m(x0) ~ exp(m * growth) / 2
+            const int cap = (int)fmin(1e6, floor(log(2e9) / growth));
+            next_degree = min(next_degree, max(4, cap));
+        }
+    }
     e.degree_used = next_degree;   // the coming iteration runs next_degree steps
     e.degree_next = next_degree;
     e.prev_res = worst;
