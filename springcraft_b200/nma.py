@@ -18,6 +18,15 @@ N_A = 6.02214076e23
 
 # mode subsets reaching at most this index are served by the lowest-k solver
 LOWEST_K_MAX = 58
+# Below this matrix order the dense full-spectrum solver is used even for a few modes: a 32..64-wide block
+# would span a large part of the space, where Chebyshev-filtered subspace iteration loses rank.
+LOWEST_N_MIN = 512
+
+
+def _use_lowest(enm, k_total):
+    D, _ = _kind(enm)
+    return (enm._has_model() and k_total <= LOWEST_K_MAX and D * len(enm._coord) > LOWEST_N_MIN
+            and enm._spectrum_cache.get("full") is None)
 
 
 def _kind(enm, what="GNM/ANM"):
@@ -63,7 +72,7 @@ def _low_spectrum(enm, k_total):
 def eigen(enm, *, k=None):
     """Eigenvalues (ascending) and eigenvectors as rows (nma.py:29-63)."""
     _kind(enm)
-    if k is None or not enm._has_model() or int(k) > LOWEST_K_MAX:
+    if k is None or not _use_lowest(enm, int(k)):
         # every mode (or more than the lowest-k solver's block holds): dense block-Jacobi path
         lam, modes = _full_spectrum(enm)
         if k is not None:
@@ -92,7 +101,7 @@ def _select(enm, mode_subset, ntriv):
     if any(mode_subset <= (ntriv - 1)):  # nma.py:161-165, 316-320
         raise ValueError("Trivial modes are included in the current selection. Please check your input.")
     top = int(mode_subset.max()) + 1
-    if enm._has_model() and top <= LOWEST_K_MAX and enm._spectrum_cache.get("full") is None:
+    if _use_lowest(enm, top):
         lam, modes = _low_spectrum(enm, top)
     else:
         lam, modes = _full_spectrum(enm)
@@ -144,7 +153,7 @@ def normal_mode(anm, index, amplitude, frames, movement="sine"):
         raise ValueError(f"Movement '{movement}' is unknown")
     import torch
     from . import _lib
-    if anm._has_model() and 0 <= index < LOWEST_K_MAX and anm._spectrum_cache.get("full") is None:
+    if index >= 0 and _use_lowest(anm, index + 1):
         _, modes = _low_spectrum(anm, index + 1)
     else:
         _, modes = _full_spectrum(anm)
