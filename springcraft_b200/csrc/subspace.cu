@@ -473,10 +473,14 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
     e.iters += 1;
     double worst = 0.0;
     const double scale = fmax(fabs(th[k - 1]), 1e-300);
+    bool finite = true;   // a NaN Ritz pair must never pass the convergence test (fmax drops NaNs)
     for (int q = 0; q < b; ++q) {
         const double r = sqrt(rn2[(int64_t)s * b + q]);
         resid[(int64_t)s * b + q] = r;
-        if (q < k) worst = fmax(worst, r);
+        if (q < k) {
+            worst = fmax(worst, r);
+            finite = finite && (r == r) && (th[q] == th[q]);
+        }
     }
     e.a0 = th[0];
     // repair a too small (estimated) upper bound: after a filter pass the largest Ritz value of the block
@@ -488,7 +492,7 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
     if (!(lo > e.a0)) lo = e.a0 + 0.5 * (e.ub - e.a0);
     e.lo = lo;
     bool finished = false;
-    if (worst <= tol * scale) {
+    if (finite && worst <= tol * scale) {
         e.converged = 1;
         done[s] = 1;
         finished = true;
