@@ -17,7 +17,8 @@
 
 namespace scb {
 
-constexpr int kLanczosSteps = 10;  // column-wise Lanczos steps of the spectrum-bound estimator
+constexpr int kLanczosSteps = 8;      // column-wise Lanczos steps of the spectrum-bound estimator (6: +4 % iterations, 10/12: same iterations, 1-3 % slower)
+constexpr int kLanczosStepsMax = 16;  // workspace is sized for this many (SCB_LANCZOS)
 
 struct EigWork {
     double *A, *Bf, *Cf, *HX;    // block vectors [B][N][b]; A is the canonical basis (caller's X)
@@ -47,8 +48,8 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
     w->rn2 = ar.take<double>((size_t)B * b);
     w->P = ar.take<double>((size_t)B * 8 * b);
     w->coef = ar.take<double>((size_t)B * degree_cap * 3);
-    w->lz_alpha = ar.take<double>((size_t)kLanczosSteps * B * b);
-    w->lz_beta2 = ar.take<double>((size_t)kLanczosSteps * B * b);
+    w->lz_alpha = ar.take<double>((size_t)kLanczosStepsMax * B * b);
+    w->lz_beta2 = ar.take<double>((size_t)kLanczosStepsMax * B * b);
     w->state = ar.take<EigState>(B);
     w->done = ar.take<int32_t>(B);
     w->n_active = ar.take<int32_t>(1);
@@ -104,20 +105,23 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
     // early outer iterations filter in FP32 (see spmm_paired_f32.cu); SCB_FP32=0 disables it
     int allow32 = 1;
     if (const char* env = getenv("SCB_FP32")) allow32 = atoi(env) != 0;
-    const double switch_tol = 3e-6;  // x spectrum bound: ~50x above the FP32 stagnation level (~5e-8 * ub)
+    double switch_tol = 3e-6;  // x spectrum bound: ~50x above the FP32 stagnation level (~5e-8 * ub)
+    if (const char* env = getenv("SCB_SWITCH_TOL")) switch_tol = atof(env) > 0.0 ? atof(env) : switch_tol;
+    int lz_steps = kLanczosSteps;
+    if (const char* env = getenv("SCB_LANCZOS")) lz_steps = (atoi(env) >= 2 && atoi(env) <= kLanczosStepsMax) ? atoi(env) : lz_steps;
     if (allow32) SCB_TRY(build_paired32(D, paired_capacity(B, n, P), w.pent, w.pent32, st));
     SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, w.skip32, w.skip64, allow32, degree, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
     SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
 
     // ---- spectrum bound: column-wise Lanczos on a copy of the random block (V=Bf, Vprev=Cf, W=HX)
-    if (N > 4 * kLanczosSteps) {
+    if (N > 4 * lz_steps) {
         const size_t vec_bytes = sizeof(double) * (size_t)B * N * b;
         SCB_CUDA(cudaMemcpyAsync(w.Bf, w.A, vec_bytes, cudaMemcpyDeviceToDevice, st));
         SCB_CUDA(cudaMemsetAsync(w.Cf, 0, vec_bytes, st));
         SCB_TRY(coldot(B, N, b, w.Bf, w.Bf, w.rn2, st));
         SCB_TRY(lanczos_axpy(B, N, b, 2, w.Bf, nullptr, nullptr, nullptr, nullptr, w.rn2, st));
-        for (int j = 0; j < kLanczosSteps; ++j) {
+        for (int j = 0; j < lz_steps; ++j) {
             double* aj = w.lz_alpha + (size_t)j * B * b;
             double* bj = w.lz_beta2 + (size_t)j * B * b;
             const double* bprev = j > 0 ? w.lz_beta2 + (size_t)(j - 1) * B * b : nullptr;
@@ -125,9 +129,9 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
             SCB_TRY(coldot(B, N, b, w.Bf, w.HX, aj, st));
             SCB_TRY(lanczos_axpy(B, N, b, 0, w.Bf, w.Cf, w.HX, aj, bprev, nullptr, st));
             SCB_TRY(coldot(B, N, b, w.HX, w.HX, bj, st));
-            if (j + 1 < kLanczosSteps) SCB_TRY(lanczos_axpy(B, N, b, 1, w.Bf, w.Cf, w.HX, nullptr, nullptr, bj, st));
+            if (j + 1 < lz_steps) SCB_TRY(lanczos_axpy(B, N, b, 1, w.Bf, w.Cf, w.HX, nullptr, nullptr, bj, st));
         }
-        SCB_TRY(lanczos_bound(B, b, kLanczosSteps, w.lz_alpha, w.lz_beta2, w.state, st));
+        SCB_TRY(lanczos_bound(B, b, lz_steps, w.lz_alpha, w.lz_beta2, w.state, st));
         SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
     }
 
