@@ -8,6 +8,7 @@ static thread_local char g_last_error[512] = "";
 void set_last_cuda_error(cudaError_t e, const char* file, int line) {
     snprintf(g_last_error, sizeof(g_last_error), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e),
              file, line);
+    (void)cudaGetLastError();   // clear the (non-sticky) runtime error so that the next launch check starts clean
 }
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }

@@ -4,6 +4,7 @@ The reference has no batched API (it rejects ndim != 2, interaction.py:141-142);
 this is the drop-in for the loop ``for c in confs: ANM(c, ff)...``."""
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -19,6 +20,14 @@ class EnsembleResult:
         self.modes = modes               # (B, k, N) or None; rows = modes
         self.n_pairs = n_pairs           # ordered contact pairs in the batch
         self.converged = converged
+
+
+def _chunk_limit(B):
+    """Structures per library call (SCB_ENSEMBLE_CHUNK overrides, for tests)."""
+    forced = os.environ.get("SCB_ENSEMBLE_CHUNK")
+    if forced:
+        return max(1, min(B, int(forced)))
+    return min(B, 32768)
 
 
 def _patch_of(ff, n, keep):
@@ -61,14 +70,32 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
         eig = np.empty((B, k))
         msf = np.empty((B, n))
         modes = np.empty((B, k, D * n)) if return_modes else None
-    npairs = C.c_int64(0)
-    status = handle.scb_enm_ensemble_host(
-        D, coords.ctypes.data_as(C.c_void_p), B, n, C.byref(desc), C.byref(patch) if patch is not None else None,
-        _lib.ptr(m_dev), k, tol, eig.ctypes.data_as(C.c_void_p), msf.ctypes.data_as(C.c_void_p),
-        modes.ctypes.data_as(C.c_void_p) if modes is not None else None, C.byref(npairs), _lib.stream_ptr())
-    _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
+    # The batch goes through the library in chunks: kernels index structures with blockIdx.y (<= 65,535) and a
+    # chunk's scratch must fit the device; on a CUDA out-of-memory status the chunk is halved and retried.
+    chunk = _chunk_limit(B)
+    total_pairs, converged, c0 = 0, True, 0
+    while c0 < B:
+        c1 = min(B, c0 + chunk)
+        npairs = C.c_int64(0)
+        status = handle.scb_enm_ensemble_host(
+            D, coords[c0:c1].ctypes.data_as(C.c_void_p), c1 - c0, n, C.byref(desc),
+            C.byref(patch) if patch is not None else None, _lib.ptr(m_dev), k, tol,
+            eig[c0:c1].ctypes.data_as(C.c_void_p), msf[c0:c1].ctypes.data_as(C.c_void_p),
+            modes[c0:c1].ctypes.data_as(C.c_void_p) if modes is not None else None, C.byref(npairs),
+            _lib.stream_ptr())
+        try:
+            _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
+        except RuntimeError as err:
+            if "out of memory" in str(err).lower() and chunk > 1:
+                chunk = (chunk + 1) // 2
+                torch.cuda.empty_cache()
+                continue
+            raise
+        total_pairs += int(npairs.value)
+        converged = converged and status == 0
+        c0 = c1
     del keep
-    return EnsembleResult(eig, msf, modes, int(npairs.value), status == 0)
+    return EnsembleResult(eig, msf, modes, total_pairs, converged)
 
 
 def _ensemble_all_modes(coords, force_field, D, masses, return_modes):

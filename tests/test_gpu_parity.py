@@ -444,6 +444,23 @@ def test_ensemble_all_modes_vs_oracle():
         assert np.allclose(gres.msf[q], orc.mean_square_fluctuation(lam, vec.T, 1), rtol=PROD_RTOL, atol=0)
 
 
+def test_ensemble_chunked_equals_single_call(monkeypatch):
+    """`enm_ensemble` feeds the library in chunks (grid limits, device memory): forcing 3-structure chunks
+    must reproduce the single-call result for every conformation, uneven tail included."""
+    ref = golden("ref_c3_chain300.npz")
+    coords = np.stack([orc.perturbed_conformation(ref["base"], c) for c in range(8)])
+    atoms = sc.AtomArray(ref["base"], ref["res_name"], ref["chain_id"], ref["res_id"])
+    ff = sc.TabulatedForceField.e_anm(atoms)
+    whole = sc.enm_ensemble(coords, ff, k=20, return_modes=True)
+    monkeypatch.setenv("SCB_ENSEMBLE_CHUNK", "3")
+    parts = sc.enm_ensemble(coords, ff, k=20, return_modes=True)
+    assert parts.converged and whole.converged and parts.n_pairs == whole.n_pairs
+    assert np.allclose(parts.eigenvalues, whole.eigenvalues, rtol=1e-10, atol=0)
+    assert np.allclose(parts.msf, whole.msf, rtol=1e-8, atol=0)
+    for q in range(8):
+        assert subspace_sin(parts.modes[q], whole.modes[q]) < ANGLE_TOL
+
+
 def test_degenerate_inputs():
     """No contacts at all, and structures of 2-3 nodes (edge cases of the contact / assembly kernels)."""
     rng = np.random.default_rng(1)
