@@ -290,6 +290,9 @@ int scb_export_modes(int B, int N, int b, int k0, int m, const double *X, double
  *   eigval_host[B][k], msf_host[B][n], modes_host[B][k][N] or NULL
  *   k non-trivial modes (indices ntriv..ntriv+k-1 of the reference's ordering)
  * Returns 0 or a negative scb_status; n_pairs_out receives P (may be NULL).
+ * B <= 65,535 per call (structures are indexed by blockIdx.y; SCB_ERR_UNSUPPORTED beyond): callers
+ * split larger ensembles, as springcraft_b200.enm_ensemble does.  Systems with D*n <= 8*block take the
+ * dense full-spectrum solver instead of subspace iteration.
  * ------------------------------------------------------------------------- */
 /* same path with DEVICE buffers (xyz SoA [B][3][n]; outputs on the device) */
 int scb_enm_ensemble(int D, const double *xyz, int B, int n, const scb_ff_desc *ff,

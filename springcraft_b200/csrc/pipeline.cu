@@ -89,6 +89,7 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
                                 double* msf, double* modes, int32_t* iters, int64_t* n_pairs_out, void* stream) {
     if (!xyz || !ff || !eigval || !msf || B < 1 || n < 1 || k < 1 || (D != 1 && D != 3)) return SCB_ERR_INVALID;
     if (ff->cutoff_sq < 0.0) return SCB_ERR_UNSUPPORTED;  // all-pairs force fields: dense slab path
+    if (B > 65535) return SCB_ERR_UNSUPPORTED;   // structures are indexed by blockIdx.y: callers chunk larger batches
     configure_pool_once();
     cudaStream_t st = as_stream(stream);
     const int nz = (D == 3) ? 6 : 1;

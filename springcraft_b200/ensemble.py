@@ -140,11 +140,17 @@ def enm_ensemble_device(xyz_soa, force_field, k=20, kind="anm", masses=None, tol
                torch.empty((B, n), dtype=torch.float64, device="cuda"),
                torch.empty(B, dtype=torch.int32, device="cuda"))
     eig, msf, iters = out
-    npairs = C.c_int64(0)
-    status = handle.scb_enm_ensemble(D, _lib.ptr(xyz_soa), B, n, C.byref(desc),
-                                     C.byref(patch) if patch is not None else None, _lib.ptr(m_dev), k, tol,
-                                     _lib.ptr(eig), _lib.ptr(msf), None, _lib.ptr(iters), C.byref(npairs),
-                                     _lib.stream_ptr())
-    _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
+    total_pairs, converged = 0, True
+    chunk = _chunk_limit(B)
+    for c0 in range(0, B, chunk):       # blockIdx.y indexes structures: at most 65,535 per library call
+        c1 = min(B, c0 + chunk)
+        npairs = C.c_int64(0)
+        status = handle.scb_enm_ensemble(D, _lib.ptr(xyz_soa[c0:c1]), c1 - c0, n, C.byref(desc),
+                                         C.byref(patch) if patch is not None else None, _lib.ptr(m_dev), k, tol,
+                                         _lib.ptr(eig[c0:c1]), _lib.ptr(msf[c0:c1]), None, _lib.ptr(iters[c0:c1]),
+                                         C.byref(npairs), _lib.stream_ptr())
+        _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
+        total_pairs += int(npairs.value)
+        converged = converged and status == 0
     del keep
-    return eig, msf, iters, int(npairs.value), status == 0
+    return eig, msf, iters, total_pairs, converged
