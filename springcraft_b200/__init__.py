@@ -11,4 +11,5 @@ from .ensemble import *  # noqa: F401,F403
 from .forcefield import *  # noqa: F401,F403
 from .gnm import *  # noqa: F401,F403
 from .interaction import *  # noqa: F401,F403
-from .structure import AtomArray, BadStructureError, read_pdb_ca  # noqa: F401
+from .structure import (AtomArray, BadStructureError, read_cif_ca, read_pdb_ca,  # noqa: F401
+                        read_pdb_ca_models)

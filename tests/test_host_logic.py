@@ -239,3 +239,82 @@ def test_read_pdb_ca(tmp_path):
     assert np.allclose(ca.coord[1], [-4.923, 4.002, -2.452])
     ff = sc.TabulatedForceField.e_anm(ca)
     assert ff.natoms == 3 and ff._bonded_next.tolist() == [1, 0, 0]
+
+
+def test_read_pdb_ca_models(tmp_path):
+    """Multi-model PDB (NMR bundle / trajectory dump) -> (atoms, coords[models][n][3]) for enm_ensemble."""
+    def model(k, shift, extra=""):
+        return [f"MODEL     {k:4d}",
+                f"ATOM      1  N   ASN A   1      -8.901   4.127  -0.555  1.00  0.00           N  ",
+                f"ATOM      2  CA  ASN A   1    {-8.608 + shift:8.3f}   3.135  -1.618  1.00  0.00           C  ",
+                f"ATOM      3  CA  LEU A   2    {-4.923 + shift:8.3f}   4.002  -2.452  1.00  0.00           C  ",
+                f"ATOM      4  CA  TYR B   3    {-3.690 + shift:8.3f}   2.738  -5.833  1.00  0.00           C  "] + \
+               ([extra] if extra else []) + ["ENDMDL"]
+    path = tmp_path / "bundle.pdb"
+    path.write_text("\n".join(model(1, 0.0) + model(2, 0.5) + model(3, 1.0)) + "\n")
+    atoms, coords = sc.read_pdb_ca_models(str(path))
+    assert len(atoms) == 3 and coords.shape == (3, 3, 3) and coords.dtype == np.float64
+    assert np.allclose(coords[:, 0, 0], [-8.608, -8.108, -7.608]) and np.allclose(coords[0], atoms.coord)
+    assert atoms.chain_id.tolist() == ["A", "A", "B"]
+    bad = tmp_path / "bad.pdb"
+    extra = "ATOM      5  CA  GLY B   4       0.000   0.000   0.000  1.00  0.00           C  "
+    bad.write_text("\n".join(model(1, 0.0) + model(2, 0.5, extra)) + "\n")
+    with pytest.raises(sc.BadStructureError):
+        sc.read_pdb_ca_models(str(bad))
+    single = tmp_path / "single.pdb"
+    single.write_text("\n".join(model(1, 0.0)[1:-1]) + "\n")          # no MODEL/ENDMDL records
+    atoms1, coords1 = sc.read_pdb_ca_models(str(single))
+    assert coords1.shape == (1, 3, 3) and len(atoms1) == 3
+
+
+def test_read_cif_ca(tmp_path):
+    """mmCIF (text) CA reader: quoted atom names, alternate locations, hetero calcium, second model."""
+    cif = """data_MINI
+#
+loop_
+_entity.id
+_entity.type
+1 polymer
+#
+loop_
+_atom_site.group_PDB
+_atom_site.id
+_atom_site.type_symbol
+_atom_site.label_atom_id
+_atom_site.label_alt_id
+_atom_site.label_comp_id
+_atom_site.label_asym_id
+_atom_site.label_seq_id
+_atom_site.Cartn_x
+_atom_site.Cartn_y
+_atom_site.Cartn_z
+_atom_site.auth_seq_id
+_atom_site.auth_asym_id
+_atom_site.pdbx_PDB_model_num
+ATOM   1 N  N     . ASN A 1 -8.901 4.127 -0.555 11 X 1
+ATOM   2 C  CA    . ASN A 1 -8.608 3.135 -1.618 11 X 1
+ATOM   3 O  "O5'" . ASN A 1 -7.000 3.000 -1.000 11 X 1
+ATOM   4 C  CA    A LEU A 2 -4.923 4.002 -2.452 12 X 1
+ATOM   5 C  CA    B LEU A 2 -4.900 4.000 -2.400 12 X 1
+HETATM 6 CA CA    . CA  B . 0.000 0.000 0.000 101 X 1
+ATOM   7 C  CA    . TYR C 3 -3.690 2.738 -5.833 13 Y 1
+ATOM   8 C  CA    . ASN A 1 0.000 0.000 0.000 11 X 2
+#
+loop_
+_other.id
+1
+"""
+    path = tmp_path / "mini.cif"
+    path.write_text(cif)
+    ca = sc.read_cif_ca(str(path))
+    assert len(ca) == 3
+    assert ca.res_name.tolist() == ["ASN", "LEU", "TYR"] and ca.chain_id.tolist() == ["X", "X", "Y"]
+    assert ca.res_id.tolist() == [11, 12, 13] and ca.coord.dtype == np.float32
+    assert np.allclose(ca.coord[1], [-4.923, 4.002, -2.452])
+    assert len(sc.read_cif_ca(str(path), model=2)) == 1
+    ff = sc.TabulatedForceField.e_anm(ca)
+    assert ff.natoms == 3 and ff._bonded_next.tolist() == [1, 0, 0]
+    empty = tmp_path / "empty.cif"
+    empty.write_text("data_X\n#\n")
+    with pytest.raises(sc.BadStructureError):
+        sc.read_cif_ca(str(empty))
