@@ -335,8 +335,81 @@ def ref_synthetic():
          gnm_msf=gnm.mean_square_fluctuation())
 
 
+FUZZ_KINDS = ["invariant", "hinsen", "hinsen_nocut", "pfree", "pfree_nocut", "e_anm", "e_anm_mean", "e_anm_mj",
+              "e_anm_ke", "sd_enm", "d_enm", "s_enm_10", "s_enm_13"]
+AA3 = ["ALA", "CYS", "ASP", "GLU", "PHE", "GLY", "HIS", "ILE", "LYS", "LEU",
+       "MET", "ASN", "PRO", "GLN", "ARG", "SER", "THR", "VAL", "TRP", "TYR"]
+
+
+def fuzz_force_field(kind, cutoff, atoms):
+    if kind == "invariant":
+        return springcraft.InvariantForceField(cutoff)
+    if kind == "hinsen":
+        return springcraft.HinsenForceField(cutoff)
+    if kind == "hinsen_nocut":
+        return springcraft.HinsenForceField()
+    if kind == "pfree":
+        return springcraft.ParameterFreeForceField(cutoff)
+    if kind == "pfree_nocut":
+        return springcraft.ParameterFreeForceField()
+    if kind == "e_anm_mean":
+        return springcraft.TabulatedForceField.e_anm(atoms, nonbonded_mean=True)
+    return getattr(springcraft.TabulatedForceField, kind)(atoms)
+
+
+def ref_fuzz():
+    """Seeded random small cases (chains with breaks, several chain ids, gaps in the residue numbering, random
+    sequences, every force-field kind, random patches and masses) through the unmodified reference."""
+    rng = np.random.default_rng(20260)
+    out = {"n_cases": np.array(26)}
+    for i in range(26):
+        n = int(rng.integers(10, 41))
+        coord = orc.synthetic_chain(n, seed=100 + i, jitter=0.4).astype(np.float32)
+        res_name = rng.choice(AA3, size=n)
+        nchain = int(rng.integers(1, 4))
+        cuts = np.sort(rng.choice(np.arange(2, n - 1), size=nchain - 1, replace=False)) if nchain > 1 else []
+        chain_id = np.array(["A"] * n)
+        for c, start in enumerate(cuts):
+            chain_id[start:] = "ABC"[c + 1]
+        res_id = np.arange(1, n + 1)
+        for g in rng.choice(np.arange(1, n), size=int(rng.integers(0, 3)), replace=False):
+            res_id[g:] += int(rng.integers(1, 4))          # numbering gaps: no bonded constant across them
+        atoms = make_atoms(coord, res_name, chain_id, res_id)
+        kind = FUZZ_KINDS[i % len(FUZZ_KINDS)]
+        cutoff = float(np.round(rng.uniform(6.5, 14.0), 2))
+        ff = fuzz_force_field(kind, cutoff, atoms)
+        patched = bool(i % 2)
+        shutdown = pair_off = pair_on = fcs = None
+        if patched:
+            shutdown = rng.choice(n, size=int(rng.integers(0, 3)), replace=False)
+            pair_off = np.array([rng.choice(n, size=2, replace=False) for _ in range(2)])
+            pair_on = np.array([rng.choice(n, size=2, replace=False) for _ in range(2)])
+            fcs = np.round(rng.uniform(0.2, 9.0, size=2), 3)
+            ff = springcraft.PatchedForceField(ff, contact_shutdown=shutdown if len(shutdown) else None,
+                                               contact_pair_off=pair_off, contact_pair_on=pair_on, force_constants=fcs)
+        masses = rng.uniform(60.0, 200.0, size=n) if i % 3 == 0 else None
+        pre = f"case{i}/"
+        out[pre + "coord"], out[pre + "res_name"], out[pre + "chain_id"], out[pre + "res_id"] = \
+            coord, res_name, chain_id, res_id
+        out[pre + "kind"], out[pre + "cutoff"], out[pre + "patched"] = np.array(kind), np.array(cutoff), np.array(patched)
+        if patched:
+            out[pre + "shutdown"], out[pre + "pair_off"], out[pre + "pair_on"], out[pre + "pair_on_fc"] = \
+                shutdown, pair_off, pair_on, fcs
+        if masses is not None:
+            out[pre + "masses"] = masses
+        H, pairs = springcraft.compute_hessian(atoms.coord, ff)
+        K, _ = springcraft.compute_kirchhoff(atoms.coord, ff)
+        out[pre + "pairs"], out[pre + "hessian"], out[pre + "kirchhoff"] = pairs, H, K
+        anm = springcraft.ANM(atoms, ff, masses=masses)
+        gnm = springcraft.GNM(atoms, ff, masses=masses)
+        out[pre + "anm_matrix"], out[pre + "gnm_matrix"] = anm.hessian, gnm.kirchhoff
+        out[pre + "anm_eigval"], out[pre + "gnm_eigval"] = anm.eigen()[0], gnm.eigen()[0]
+        out[pre + "anm_msf"], out[pre + "gnm_msf"] = anm.mean_square_fluctuation(), gnm.mean_square_fluctuation()
+    save("ref_fuzz.npz", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["structures", "ref_1l2y", "ref_two_chain", "thirdparty",
-                             "ref_random500", "ref_7cal", "ref_synthetic"]
+                             "ref_random500", "ref_7cal", "ref_synthetic", "ref_fuzz"]
     for w in which:
         globals()[w]()

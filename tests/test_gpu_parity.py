@@ -461,6 +461,58 @@ def test_ensemble_chunked_equals_single_call(monkeypatch):
         assert subspace_sin(parts.modes[q], whole.modes[q]) < ANGLE_TOL
 
 
+def _fuzz_force_field(ref, i, atoms):
+    pre = f"case{i}/"
+    kind, cutoff = str(ref[pre + "kind"]), float(ref[pre + "cutoff"])
+    if kind == "invariant":
+        ff = sc.InvariantForceField(cutoff)
+    elif kind == "hinsen":
+        ff = sc.HinsenForceField(cutoff)
+    elif kind == "hinsen_nocut":
+        ff = sc.HinsenForceField()
+    elif kind == "pfree":
+        ff = sc.ParameterFreeForceField(cutoff)
+    elif kind == "pfree_nocut":
+        ff = sc.ParameterFreeForceField()
+    elif kind == "e_anm_mean":
+        ff = sc.TabulatedForceField.e_anm(atoms, nonbonded_mean=True)
+    else:
+        ff = getattr(sc.TabulatedForceField, kind)(atoms)
+    if bool(ref[pre + "patched"]):
+        sd = ref[pre + "shutdown"]
+        ff = sc.PatchedForceField(ff, contact_shutdown=sd if len(sd) else None, contact_pair_off=ref[pre + "pair_off"],
+                                  contact_pair_on=ref[pre + "pair_on"], force_constants=ref[pre + "pair_on_fc"])
+    return ff
+
+
+@pytest.mark.parametrize("i", range(26))
+def test_fuzz_cases_vs_reference(i):
+    """26 seeded random cases generated by the unmodified reference (chain breaks, numbering gaps, random
+    sequences, every force-field kind, random patches, masses): contacts exact, matrices <= 1e-12, spectra
+    <= 1e-8 of the spectral radius, MSF <= 1e-8 where the matrix has no extra (near-)null directions."""
+    ref = golden("ref_fuzz.npz")
+    pre = f"case{i}/"
+    atoms = sc.AtomArray(ref[pre + "coord"], ref[pre + "res_name"], ref[pre + "chain_id"], ref[pre + "res_id"])
+    ff = _fuzz_force_field(ref, i, atoms)
+    masses = ref[pre + "masses"] if pre + "masses" in ref else None
+    H, pairs = sc.compute_hessian(atoms.coord, ff)
+    K, _ = sc.compute_kirchhoff(atoms.coord, ff)
+    assert np.array_equal(pairs, ref[pre + "pairs"])
+    assert rel_err(K, ref[pre + "kirchhoff"]) <= HESS_RTOL and rel_err(H, ref[pre + "hessian"]) <= HESS_RTOL
+    if str(ref[pre + "kind"]) == "invariant":
+        assert np.array_equal(K, ref[pre + "kirchhoff"])
+    for cls, key, ntriv in ((sc.ANM, "anm", 6), (sc.GNM, "gnm", 1)):
+        enm = cls(atoms, ff, masses=masses)
+        M = enm.hessian if key == "anm" else enm.kirchhoff
+        assert rel_err(M, ref[pre + f"{key}_matrix"]) <= HESS_RTOL
+        want = ref[pre + f"{key}_eigval"]
+        lam, modes = enm.eigen()
+        assert np.allclose(lam, want, rtol=0, atol=EIG_RTOL * np.abs(want).max())
+        assert np.abs(M @ modes.T - modes.T * lam).max() <= 1e-10 * np.abs(want).max()
+        if want[ntriv] > 1e-3 * want[-1]:
+            assert np.allclose(enm.mean_square_fluctuation(), ref[pre + f"{key}_msf"], rtol=PROD_RTOL, atol=0)
+
+
 def test_degenerate_inputs():
     """No contacts at all, and structures of 2-3 nodes (edge cases of the contact / assembly kernels)."""
     rng = np.random.default_rng(1)

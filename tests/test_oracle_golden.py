@@ -222,3 +222,50 @@ def test_thirdparty_1l2y(structures):
     lam, modes = orc.eigen(H)
     assert np.allclose(orc.mean_square_fluctuation(lam, modes, 3), tp["biophysconnector_anm_eanm_bfacs_1l2y"])
     assert np.allclose(lam[6:], tp["biophysconnector_anm_eanm_evals_1l2y"][6:])
+
+
+def _fuzz_spec(ref, i):
+    pre = f"case{i}/"
+    kind, cutoff = str(ref[pre + "kind"]), float(ref[pre + "cutoff"])
+    s = (ref[pre + "res_name"], ref[pre + "chain_id"], ref[pre + "res_id"])
+    if kind == "invariant":
+        spec = orc.FFSpec("invariant", cutoff)
+    elif kind in ("hinsen", "pfree"):
+        spec = orc.FFSpec(kind, cutoff)
+    elif kind in ("hinsen_nocut", "pfree_nocut"):
+        spec = orc.FFSpec(kind.split("_")[0], None)
+    elif kind == "e_anm_mean":
+        spec = orc.preset_spec("e_anm", *s, nonbonded_mean=True)
+    else:
+        spec = orc.preset_spec(kind, *s)
+    if bool(ref[pre + "patched"]):
+        spec.patched = True
+        sd = ref[pre + "shutdown"]
+        spec.shutdown = sd if len(sd) else None
+        spec.pair_off, spec.pair_on, spec.pair_on_fc = ref[pre + "pair_off"], ref[pre + "pair_on"], ref[pre + "pair_on_fc"]
+    return spec
+
+
+@pytest.mark.parametrize("i", range(26))
+def test_fuzz_cases_bit_exact(i):
+    """26 seeded random cases (chain breaks, numbering gaps, random sequences, all force-field kinds, random
+    patches and masses) generated by the unmodified reference (tests/golden/make_golden.py::ref_fuzz)."""
+    ref = golden("ref_fuzz.npz")
+    pre = f"case{i}/"
+    spec = _fuzz_spec(ref, i)
+    coord = ref[pre + "coord"]
+    masses = ref[pre + "masses"] if pre + "masses" in ref else None
+    H, pairs = orc.compute_hessian(coord, spec)
+    K, _ = orc.compute_kirchhoff(coord, spec)
+    assert np.array_equal(pairs, ref[pre + "pairs"])
+    assert np.array_equal(K, ref[pre + "kirchhoff"])
+    assert np.array_equal(H, ref[pre + "hessian"])
+    Hm, _ = orc.compute_hessian(coord, spec, masses=masses)
+    Km, _ = orc.compute_kirchhoff(coord, spec, masses=masses)
+    assert np.array_equal(Hm, ref[pre + "anm_matrix"]) and np.array_equal(Km, ref[pre + "gnm_matrix"])
+    lam, modes = orc.eigen(Hm)
+    assert np.array_equal(lam, ref[pre + "anm_eigval"])
+    assert np.allclose(orc.mean_square_fluctuation(lam, modes, 3), ref[pre + "anm_msf"], rtol=1e-11)
+    lam, modes = orc.eigen(Km)
+    assert np.array_equal(lam, ref[pre + "gnm_eigval"])
+    assert np.allclose(orc.mean_square_fluctuation(lam, modes, 1), ref[pre + "gnm_msf"], rtol=1e-11)
