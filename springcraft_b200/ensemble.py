@@ -37,7 +37,8 @@ def _patch_of(ff, n, keep):
 
 def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, return_modes=False,
                  pinned_out=None):
-    """ANM/GNM of B conformations: coords (B, n, 3) host array (float64).
+    """ANM/GNM of B conformations: coords (B, n, 3) host array (float64) or an object with such a
+    ``coord`` attribute (biotite ``AtomArrayStack``).
 
     Returns the k lowest NON-trivial modes' eigenvalues (reference indices
     6..6+k-1 for ANM, 1..k for GNM) and ``mean_square_fluctuation(mode_subset=
@@ -48,10 +49,11 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
     nma.py:145-151): dense matrices go through the batched full-spectrum solver
     in chunks; two orders of magnitude slower than a small k."""
     import torch
-    handle = _lib.require_device()
-    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    # a biotite AtomArrayStack (or anything with a (B,n,3) ``coord`` attribute) is accepted as well
+    coords = np.ascontiguousarray(getattr(coords, "coord", coords), dtype=np.float64)
     if coords.ndim != 3 or coords.shape[2] != 3:
         raise ValueError(f"Expected coordinates with shape (B,n,3), got {coords.shape}")
+    handle = _lib.require_device()
     B, n = int(coords.shape[0]), int(coords.shape[1])
     D = 3 if kind == "anm" else 1
     if k is None:

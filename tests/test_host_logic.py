@@ -318,3 +318,21 @@ _other.id
     empty.write_text("data_X\n#\n")
     with pytest.raises(sc.BadStructureError):
         sc.read_cif_ca(str(empty))
+
+
+def test_ensemble_argument_checks_come_before_the_device():
+    """Shape errors are the reference's ValueError (interaction.py:141-142) even without a GPU; a valid call
+    without a device fails loudly (no CPU fallback)."""
+    with pytest.raises(ValueError):
+        sc.enm_ensemble(np.zeros((4, 10, 2)), sc.InvariantForceField(7.0))
+    with pytest.raises(ValueError):
+        sc.enm_ensemble(np.zeros((10, 3)), sc.InvariantForceField(7.0))
+
+    class Stack:                       # stands in for biotite's AtomArrayStack
+        coord = np.zeros((2, 10, 4), dtype=np.float32)
+    with pytest.raises(ValueError):
+        sc.enm_ensemble(Stack(), sc.InvariantForceField(7.0))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            sc.enm_ensemble(np.zeros((2, 10, 3)), sc.InvariantForceField(7.0))
