@@ -13,9 +13,11 @@
 // The host polls one int32 (number of active structures) per outer iteration.
 #include <stdlib.h>
 
-#include "subspace.cuh"
+#include "resident.cuh"
 
 namespace scb {
+
+int64_t resident_rec_pad_of(int n, int cols);
 
 constexpr int kLanczosSteps = 8;      // column-wise Lanczos steps of the spectrum-bound estimator (6: +4 % iterations, 10/12: same iterations, 1-3 % slower)
 constexpr int kLanczosStepsMax = 16;  // workspace is sized for this many (SCB_LANCZOS)
@@ -31,6 +33,7 @@ struct EigWork {
     char* pent32;             // single-precision copy of the records (spmm_paired_f32.cu)
     float *Xa32, *Xb32, *Xc32;
     int32_t *skip32, *skip64; // per-structure precision of the next filter
+    ResLayout res;            // structure-resident operator (resident.cuh); res.cols == 0: not eligible
 };
 
 static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, int degree_cap, double* X,
@@ -63,6 +66,19 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
     w->skip32 = ar.take<int32_t>(B);
     w->skip64 = ar.take<int32_t>(B);
     (void)nz;
+    // structure-resident path (ANM ensembles of small structures)
+    ResLayout& L = w->res;
+    L.cols = (D == 3) ? resident_cols(n, b) : 0;
+    if (L.cols > 0) {
+        L.rpw = 128 / L.cols;
+        L.G = ((n + 1) / 2 + L.rpw - 1) / L.rpw;
+        L.rec_pad = resident_rec_pad_of(n, L.cols);
+        L.rec = ar.take<ResRec>(resident_capacity(B, n, P, L.cols));
+        L.gstart = ar.take<int32_t>((size_t)B * (L.G + 1));
+        L.order = ar.take<uint16_t>((size_t)B * L.G * L.rpw);
+        L.diag32 = ar.take<float>((size_t)B * n * 12);
+        L.flag = ar.take<int32_t>(1);
+    }
     return ar.off;
 }
 
@@ -109,6 +125,17 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
     if (const char* env = getenv("SCB_SWITCH_TOL")) switch_tol = atof(env) > 0.0 ? atof(env) : switch_tol;
     int lz_steps = kLanczosSteps;
     if (const char* env = getenv("SCB_LANCZOS")) lz_steps = (atoi(env) >= 2 && atoi(env) <= kLanczosStepsMax) ? atoi(env) : lz_steps;
+    // structure-resident residual-form path (resident.cuh): ANM blocks of the form -v v^T, structure fits in smem
+    bool resident = w.res.cols > 0;
+    if (const char* env = getenv("SCB_RESIDENT")) resident = resident && atoi(env) != 0;
+    if (resident) {
+        SCB_TRY(resident_build(B, n, rowptr, col, offdiag, diag, w.res, st));
+        int32_t bad = 0;
+        SCB_CUDA(cudaMemcpyAsync(&bad, w.res.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        if (bad) resident = false;   // a block with positive t (negative force constant): general 3x3 kernels
+    }
+    if (resident) allow32 = 0;
     if (allow32) SCB_TRY(build_paired32(D, paired_capacity(B, n, P), w.pent, w.pent32, st));
     SCB_TRY(state_init(B, gersh, w.state, w.done, w.n_active, w.skip32, w.skip64, allow32, degree, st));
     SCB_TRY(rand_init((int64_t)B * N * b, seed, w.A, st));
@@ -135,11 +162,44 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
     }
 
-    int32_t* h_active = nullptr;
-    SCB_CUDA(cudaMallocHost(&h_active, sizeof(int32_t)));
+    // one pinned word per host thread for the convergence poll (allocated once, reused by every call)
+    static thread_local int32_t* h_active = nullptr;
+    if (!h_active) SCB_CUDA(cudaMallocHost(&h_active, sizeof(int32_t)));
     *h_active = B;
     int status = SCB_OK;
     double* cur = w.A;  // block to orthonormalise at the top of the Rayleigh-Ritz stage
+    if (resident) {
+        // Per outer iteration: HX (FP64) -> Rayleigh-Ritz of the pencil (X^T H X, X^T X) -> residuals ->
+        // convergence / filter bounds -> ONE launch of the structure-resident FP32 filter, which returns the
+        // deflated block X + |r| z.  The corrected block is nearly orthonormal (z ~ the error of X), so no
+        // separate orthonormalisation pass is needed: the Cholesky factor of X^T X inside rr_kernel does it.
+        if ((status = deflate(B, N, b, nz, Z, w.A, w.P, nullptr, st)) != SCB_OK) return status;
+        for (int outer = 0; outer <= max_outer; ++outer) {
+            if ((status = apply(w.A, nullptr, w.HX, nullptr, 0)) != SCB_OK) break;
+            if ((status = gram(B, N, b, w.A, w.A, w.S, done, st)) != SCB_OK) break;
+            if ((status = gram(B, N, b, w.A, w.HX, w.T, done, st)) != SCB_OK) break;
+            if ((status = small_rr(B, b, w.S, w.T, w.theta, w.Cm, done, 1, st)) != SCB_OK) break;
+            if ((status = rotate(B, N, b, w.Cm, w.A, w.A, w.HX, w.HX, done, st)) != SCB_OK) break;
+            if ((status = zero_active_rn2(B, b, w.rn2, done, st)) != SCB_OK) break;
+            if ((status = residual_norms(B, N, b, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
+            if ((status = state_update(B, b, k, tol, w.theta, w.rn2, w.state, w.done, w.n_active, resid, w.skip32,
+                                       w.skip64, 0, switch_tol, degree, st)) != SCB_OK)
+                break;
+            if (cudaMemcpyAsync(h_active, w.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) {
+                set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+                status = SCB_ERR_CUDA;
+                break;
+            }
+            if (*h_active == 0 || outer == max_outer) break;
+            if ((status = resident_filter(B, n, b, rowptr, w.res, w.A, w.HX, w.theta, w.rn2, w.state, done, Z, nz,
+                                          w.A, st)) != SCB_OK)
+                break;
+        }
+        if (status != SCB_OK) return status;
+        SCB_TRY(gather_results(B, b, w.theta, w.state, eigval, iters, st));
+        return *h_active == 0 ? SCB_OK : SCB_ERR_NOT_CONVERGED;
+    }
     for (int outer = 0; outer <= max_outer; ++outer) {
         if (outer > 0) {
             // ---- 1. Chebyshev filter of degree `degree` applied to the basis in A
@@ -199,7 +259,6 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         if (*h_active == 0) break;
     }
     const int active = *h_active;
-    cudaFreeHost(h_active);
     if (status != SCB_OK) return status;
     SCB_TRY(gather_results(B, b, w.theta, w.state, eigval, iters, st));
     return active == 0 ? SCB_OK : SCB_ERR_NOT_CONVERGED;

@@ -1,0 +1,346 @@
+// Structure-resident Chebyshev filter in residual form (see resident.cuh).
+//
+// One CTA per (structure, group of COLS block columns).  The CTA keeps three N x COLS single-precision arrays in
+// shared memory for the whole filter: z_k (gather source), z_{k-1} (overwritten by z_{k+1}) and the normalised
+// residual.  A warp owns one group of row pairs; a lane owns (row pair, 4 columns) and walks the pair's records:
+//     s = v . z_col      (3 FMA per row and column)        acc += v s   (3 FMA)      [H_ij = -v v^T]
+// then z_{k+1} = A_k ((H - c) z_k + r) - B_k z_{k-1} with per-column coefficients A_k = 2 rho_k / e,
+// B_k = rho_{k-1} rho_k, rho_k = T_k(x)/T_{k+1}(x) at x = (theta - c)/e.  After `degree` steps the lane writes
+// X + |r| z (FP64), deflated against the analytic null space, back to global memory.
+#include "resident.cuh"
+
+namespace scb {
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// one record against the lane's 4 columns: acc[h][a] (+)= v_h[a] * (v_h . z)
+template <int COLS>
+__device__ __forceinline__ void rec_apply(const float4 ra, const float4 rb, const float* __restrict__ ZA, int c0,
+                                          float2 (&acc)[2][3][2]) {
+    const int col = __float_as_int(ra.x);
+    const float4* zp = reinterpret_cast<const float4*>(ZA + col * (3 * COLS) + c0);
+    const float4 z0 = zp[0], z1 = zp[COLS / 4], z2 = zp[2 * (COLS / 4)];
+    const float2 z0l = f2(z0.x, z0.y), z0h = f2(z0.z, z0.w);
+    const float2 z1l = f2(z1.x, z1.y), z1h = f2(z1.z, z1.w);
+    const float2 z2l = f2(z2.x, z2.y), z2h = f2(z2.z, z2.w);
+    {
+        const float2 vx = f2(ra.y, ra.y), vy = f2(ra.z, ra.z), vz = f2(ra.w, ra.w);
+        float2 sl = __fmul2_rn(vx, z0l), sh = __fmul2_rn(vx, z0h);
+        sl = __ffma2_rn(vy, z1l, sl); sh = __ffma2_rn(vy, z1h, sh);
+        sl = __ffma2_rn(vz, z2l, sl); sh = __ffma2_rn(vz, z2h, sh);
+        acc[0][0][0] = __ffma2_rn(vx, sl, acc[0][0][0]); acc[0][0][1] = __ffma2_rn(vx, sh, acc[0][0][1]);
+        acc[0][1][0] = __ffma2_rn(vy, sl, acc[0][1][0]); acc[0][1][1] = __ffma2_rn(vy, sh, acc[0][1][1]);
+        acc[0][2][0] = __ffma2_rn(vz, sl, acc[0][2][0]); acc[0][2][1] = __ffma2_rn(vz, sh, acc[0][2][1]);
+    }
+    {
+        const float2 vx = f2(rb.x, rb.x), vy = f2(rb.y, rb.y), vz = f2(rb.z, rb.z);
+        float2 sl = __fmul2_rn(vx, z0l), sh = __fmul2_rn(vx, z0h);
+        sl = __ffma2_rn(vy, z1l, sl); sh = __ffma2_rn(vy, z1h, sh);
+        sl = __ffma2_rn(vz, z2l, sl); sh = __ffma2_rn(vz, z2h, sh);
+        acc[1][0][0] = __ffma2_rn(vx, sl, acc[1][0][0]); acc[1][0][1] = __ffma2_rn(vx, sh, acc[1][0][1]);
+        acc[1][1][0] = __ffma2_rn(vy, sl, acc[1][1][0]); acc[1][1][1] = __ffma2_rn(vy, sh, acc[1][1][1]);
+        acc[1][2][0] = __ffma2_rn(vz, sl, acc[1][2][0]); acc[1][2][1] = __ffma2_rn(vz, sh, acc[1][2][1]);
+    }
+}
+
+// warp -> group: the longest groups go to the highest warp ids (issue priority), snaked over the 4 sub-partitions
+__device__ __forceinline__ int warp_group(int warp, int nwarps) {
+    const int kq = warp >> 2, smsp = warp & 3;
+    const int k = (nwarps >> 2) - 1 - kq;
+    const int r = (k & 1) ? smsp : 3 - smsp;
+    return 4 * k + r;
+}
+
+// acc (= sum v (v.z) over the records, i.e. -(H_offdiag z)) -> (H z) rows of the lane's two nodes, 4 columns
+template <int COLS>
+__device__ __forceinline__ void walk_records(const float4* __restrict__ rp, int iters, int stride4,
+                                             const float* __restrict__ ZA, int c0, float2 (&acc)[2][3][2]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { acc[h][a][0] = f2(0.f, 0.f); acc[h][a][1] = f2(0.f, 0.f); }
+    if (iters <= 0) return;
+    float4 r0a = __ldg(rp), r0b = __ldg(rp + 1);
+    float4 r1a = __ldg(rp + stride4), r1b = __ldg(rp + stride4 + 1);
+    for (int it = 0; it < iters; it += 2) {
+        float4 n0a = r0a, n0b = r0b, n1a = r1a, n1b = r1b;
+        if (it + 2 < iters) {
+            const float4* np = rp + (size_t)(it + 2) * stride4;
+            n0a = __ldg(np); n0b = __ldg(np + 1);
+            n1a = __ldg(np + stride4); n1b = __ldg(np + stride4 + 1);
+        }
+        rec_apply<COLS>(r0a, r0b, ZA, c0, acc);
+        rec_apply<COLS>(r1a, r1b, ZA, c0, acc);
+        r0a = n0a; r0b = n0b; r1a = n1a; r1b = n1b;
+    }
+}
+
+// (H z)[row 3i+a] for node i from the negated record sum and the diagonal block
+__device__ __forceinline__ void add_diag(const float* __restrict__ dg, const float4 (&zo)[3], const float2 (&acc)[3][2],
+                                         float4 (&hz)[3]) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(dg));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(dg) + 1);
+    const float4 d2 = __ldg(reinterpret_cast<const float4*>(dg) + 2);
+    const float D[9] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        hz[a].x = fmaf(D[3 * a + 2], zo[2].x, fmaf(D[3 * a + 1], zo[1].x, fmaf(D[3 * a], zo[0].x, -acc[a][0].x)));
+        hz[a].y = fmaf(D[3 * a + 2], zo[2].y, fmaf(D[3 * a + 1], zo[1].y, fmaf(D[3 * a], zo[0].y, -acc[a][0].y)));
+        hz[a].z = fmaf(D[3 * a + 2], zo[2].z, fmaf(D[3 * a + 1], zo[1].z, fmaf(D[3 * a], zo[0].z, -acc[a][1].x)));
+        hz[a].w = fmaf(D[3 * a + 2], zo[2].w, fmaf(D[3 * a + 1], zo[1].w, fmaf(D[3 * a], zo[0].w, -acc[a][1].y)));
+    }
+}
+
+template <int COLS>
+__global__ void __launch_bounds__(kResMaxWarps * 32, 1)
+resident_filter_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __restrict__ rowptr,
+                       const ResRec* __restrict__ rec, const int32_t* __restrict__ gstart,
+                       const uint16_t* __restrict__ order, const float* __restrict__ diag32,
+                       const double* X, const double* __restrict__ HX, const double* __restrict__ theta,
+                       const double* __restrict__ rn2, const EigState* __restrict__ state,
+                       const int32_t* __restrict__ done, const double* __restrict__ Zr, int nz, double* Xout) {
+    constexpr int LPP = COLS / 4;        // lanes per row pair
+    constexpr int RPW = 32 / LPP;        // row pairs per warp (group size)
+    extern __shared__ __align__(16) float res_smem[];
+    const int64_t s = blockIdx.y;
+    if (done && done[s]) return;
+    const int N = 3 * n;
+    float* ZA = res_smem;
+    float* ZB = ZA + (size_t)N * COLS;
+    float* RH = ZB + (size_t)N * COLS;
+    float* cA = RH + (size_t)N * COLS;               // [kResDegreeCap][COLS]
+    float* cB = cA + kResDegreeCap * COLS;
+    __shared__ double s_th[COLS], s_nrm[COLS], s_inv[COLS];
+    __shared__ float s_sc0[COLS];
+    __shared__ double s_p[8 * COLS];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nwarps = blockDim.x >> 5;
+    const int cg = blockIdx.x;
+    const EigState e = state[s];
+    int deg = e.degree_next;
+    deg = deg < 2 ? 2 : (deg > kResDegreeCap ? kResDegreeCap : deg);
+    const double ehalf = 0.5 * (e.ub - e.lo), cmid = 0.5 * (e.ub + e.lo);
+    if (tid < COLS) {
+        const int gc = cg * COLS + tid;
+        const double th = fmin(theta[s * b + gc], e.lo);
+        const double nr = sqrt(fmax(rn2[s * b + gc], 0.0));
+        s_th[tid] = th;
+        s_nrm[tid] = nr;
+        s_inv[tid] = nr > 0.0 ? 1.0 / nr : 0.0;
+        const double x = (th - cmid) / ehalf;        // <= -1
+        double rho = 1.0 / x;
+        s_sc0[tid] = (float)(rho / ehalf);
+        for (int k = 1; k < deg; ++k) {
+            const double rn = 1.0 / (2.0 * x - rho);
+            cA[k * COLS + tid] = (float)(2.0 * rn / ehalf);
+            cB[k * COLS + tid] = (float)(rho * rn);
+            rho = rn;
+        }
+    }
+    __syncthreads();
+
+    const int g = warp_group(warp, nwarps);
+    const int slot = lane / LPP, q = lane % LPP;
+    const int c0 = 4 * q;                             // first local column of the lane
+    const int gc0 = cg * COLS + c0;                   // ... in the block
+    int p = 0xFFFF;
+    if (g < G) p = order[s * (int64_t)G * RPW + g * RPW + slot];
+    const bool own = p != 0xFFFF;
+    const int i0 = 2 * p;
+    const bool has1 = own && (i0 + 1 < n);
+    const double* Xs = X + s * (int64_t)N * b;
+    const double* Hs = HX + s * (int64_t)N * b;
+
+    // ---- prologue: residual of the lane's rows -> RH, z_1 -> ZA, z_0 = 0 -> ZB
+    if (own) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !has1) break;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int row = 3 * (i0 + h) + a;
+                const double2 xa = *reinterpret_cast<const double2*>(Xs + (int64_t)row * b + gc0);
+                const double2 xb = *reinterpret_cast<const double2*>(Xs + (int64_t)row * b + gc0 + 2);
+                const double2 ha = *reinterpret_cast<const double2*>(Hs + (int64_t)row * b + gc0);
+                const double2 hb = *reinterpret_cast<const double2*>(Hs + (int64_t)row * b + gc0 + 2);
+                float4 r;
+                r.x = (float)((ha.x - s_th[c0 + 0] * xa.x) * s_inv[c0 + 0]);
+                r.y = (float)((ha.y - s_th[c0 + 1] * xa.y) * s_inv[c0 + 1]);
+                r.z = (float)((hb.x - s_th[c0 + 2] * xb.x) * s_inv[c0 + 2]);
+                r.w = (float)((hb.y - s_th[c0 + 3] * xb.y) * s_inv[c0 + 3]);
+                const float4 sc = *reinterpret_cast<const float4*>(s_sc0 + c0);
+                *reinterpret_cast<float4*>(RH + row * COLS + c0) = r;
+                *reinterpret_cast<float4*>(ZA + row * COLS + c0) = make_float4(r.x * sc.x, r.y * sc.y, r.z * sc.z, r.w * sc.w);
+                *reinterpret_cast<float4*>(ZB + row * COLS + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- record stream of the warp's group
+    const int64_t start = ((rowptr[s * n] + rec_pad * s) + 7) & ~(int64_t)7;
+    const int32_t* gst = gstart + s * (int64_t)(G + 1);
+    int iters = 0;
+    const float4* rp = nullptr;
+    if (g < G) {
+        const int g0 = gst[g];
+        iters = gst[g + 1] - g0;
+        rp = reinterpret_cast<const float4*>(rec + start + (int64_t)g0 * RPW + slot);
+    }
+    constexpr int stride4 = RPW * 2;                  // float4 per iteration of the group
+    const float cm = (float)cmid;
+    const float* dg0 = diag32 + (s * n + (own ? i0 : 0)) * 12;
+
+    for (int k = 1; k < deg; ++k) {
+        if (g < G) {
+            float2 acc[2][3][2];
+            walk_records<COLS>(rp, iters, stride4, ZA, c0, acc);
+            if (own) {
+                const float4 A4 = *reinterpret_cast<const float4*>(cA + k * COLS + c0);
+                const float4 B4 = *reinterpret_cast<const float4*>(cB + k * COLS + c0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !has1) break;
+                    float4 zo[3], hz[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) zo[a] = *reinterpret_cast<const float4*>(ZA + (3 * (i0 + h) + a) * COLS + c0);
+                    add_diag(dg0 + 12 * h, zo, acc[h], hz);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const int off = (3 * (i0 + h) + a) * COLS + c0;
+                        const float4 w = *reinterpret_cast<const float4*>(ZB + off);
+                        const float4 r = *reinterpret_cast<const float4*>(RH + off);
+                        float4 o;
+                        o.x = A4.x * (fmaf(-cm, zo[a].x, hz[a].x) + r.x) - B4.x * w.x;
+                        o.y = A4.y * (fmaf(-cm, zo[a].y, hz[a].y) + r.y) - B4.y * w.y;
+                        o.z = A4.z * (fmaf(-cm, zo[a].z, hz[a].z) + r.z) - B4.z * w.z;
+                        o.w = A4.w * (fmaf(-cm, zo[a].w, hz[a].w) + r.w) - B4.w * w.w;
+                        *reinterpret_cast<float4*>(ZB + off) = o;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        float* t = ZA; ZA = ZB; ZB = t;
+    }
+
+    // ---- epilogue: X + |r| z  (FP64), deflated against the analytic null space (nz <= 8 vectors)
+    double* Xo = Xout + s * (int64_t)N * b;
+    const double* Zs = Zr ? Zr + s * (int64_t)N * nz : nullptr;
+    double pz[8][4];
+#pragma unroll
+    for (int z = 0; z < 8; ++z)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) pz[z][cc] = 0.0;
+    if (own) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !has1) break;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int row = 3 * (i0 + h) + a;
+                const float4 zf = *reinterpret_cast<const float4*>(ZA + row * COLS + c0);
+                const double2 xa = *reinterpret_cast<const double2*>(Xs + (int64_t)row * b + gc0);
+                const double2 xb = *reinterpret_cast<const double2*>(Xs + (int64_t)row * b + gc0 + 2);
+                double xn[4];
+                xn[0] = fma(s_nrm[c0 + 0], (double)zf.x, xa.x);
+                xn[1] = fma(s_nrm[c0 + 1], (double)zf.y, xa.y);
+                xn[2] = fma(s_nrm[c0 + 2], (double)zf.z, xb.x);
+                xn[3] = fma(s_nrm[c0 + 3], (double)zf.w, xb.y);
+                *reinterpret_cast<double2*>(Xo + (int64_t)row * b + gc0) = make_double2(xn[0], xn[1]);
+                *reinterpret_cast<double2*>(Xo + (int64_t)row * b + gc0 + 2) = make_double2(xn[2], xn[3]);
+                if (Zs) {
+#pragma unroll
+                    for (int z = 0; z < 8; ++z)
+                        if (z < nz) {
+                            const double zv = Zs[(int64_t)row * nz + z];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) pz[z][cc] = fma(zv, xn[cc], pz[z][cc]);
+                        }
+                }
+            }
+        }
+    }
+    if (!Zs || nz <= 0) return;
+    // fixed-order reduction: lanes of a warp (same q), then warps in index order
+    double* red = reinterpret_cast<double*>(ZB);      // [nwarps][LPP][8][4]  (ZB is free after the last barrier)
+#pragma unroll
+    for (int z = 0; z < 8; ++z)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            double v = pz[z][cc];
+#pragma unroll
+            for (int o = LPP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            pz[z][cc] = v;
+        }
+    if (slot == 0) {
+#pragma unroll
+        for (int z = 0; z < 8; ++z)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) red[((warp * LPP + q) * 8 + z) * 4 + cc] = pz[z][cc];
+    }
+    __syncthreads();
+    if (tid < 8 * COLS) {
+        const int z = tid / COLS, c = tid % COLS;
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += red[((w * LPP + c / 4) * 8 + z) * 4 + (c & 3)];
+        s_p[z * COLS + c] = t;
+    }
+    __syncthreads();
+    if (own) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !has1) break;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int row = 3 * (i0 + h) + a;
+                double2 xa = *reinterpret_cast<const double2*>(Xo + (int64_t)row * b + gc0);
+                double2 xb = *reinterpret_cast<const double2*>(Xo + (int64_t)row * b + gc0 + 2);
+#pragma unroll
+                for (int z = 0; z < 8; ++z)
+                    if (z < nz) {
+                        const double zv = Zs[(int64_t)row * nz + z];
+                        xa.x = fma(-zv, s_p[z * COLS + c0 + 0], xa.x);
+                        xa.y = fma(-zv, s_p[z * COLS + c0 + 1], xa.y);
+                        xb.x = fma(-zv, s_p[z * COLS + c0 + 2], xb.x);
+                        xb.y = fma(-zv, s_p[z * COLS + c0 + 3], xb.y);
+                    }
+                *reinterpret_cast<double2*>(Xo + (int64_t)row * b + gc0) = xa;
+                *reinterpret_cast<double2*>(Xo + (int64_t)row * b + gc0 + 2) = xb;
+            }
+        }
+    }
+}
+
+static size_t filter_smem(int n, int cols) {
+    return sizeof(float) * ((size_t)3 * 3 * n * cols + 2 * (size_t)kResDegreeCap * cols);
+}
+
+template <int COLS>
+static int launch_filter(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, const double* X,
+                         const double* HX, const double* theta, const double* rn2, const EigState* state,
+                         const int32_t* done, const double* Z, int nz, double* Xout, cudaStream_t st) {
+    const size_t smem = filter_smem(n, COLS);
+    // the opt-in is per device and cheap: set it on every launch (no process-wide "configured" flag)
+    SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nwarps = 4 * ((L.G + 3) / 4);
+    dim3 grid((unsigned)(b / COLS), (unsigned)B);
+    resident_filter_kernel<COLS><<<grid, 32 * nwarps, smem, st>>>(n, b, L.G, L.rec_pad, rowptr, L.rec, L.gstart, L.order,
+                                                                 L.diag32, X, HX, theta, rn2, state, done, Z, nz, Xout);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+int resident_filter(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, const double* X,
+                    const double* HX, const double* theta, const double* rn2, const EigState* state,
+                    const int32_t* done, const double* Z, int nz, double* Xout, cudaStream_t st) {
+    if (nz > 8) return SCB_ERR_UNSUPPORTED;
+    if (L.cols == 16) return launch_filter<16>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, st);
+    if (L.cols == 8) return launch_filter<8>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, st);
+    if (L.cols == 4) return launch_filter<4>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, st);
+    return SCB_ERR_UNSUPPORTED;
+}
+
+}  // namespace scb
