@@ -78,6 +78,7 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
         L.order = ar.take<uint16_t>((size_t)B * L.G * L.rpw);
         L.diag32 = ar.take<float>((size_t)B * n * 12);
         L.flag = ar.take<int32_t>(1);
+        L.est = ar.take<double>(B);
     }
     return ar.off;
 }
@@ -142,7 +143,11 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
     SCB_CUDA(cudaMemsetAsync(w.rn2, 0, sizeof(double) * (size_t)B * b, st));
 
     // ---- spectrum bound: column-wise Lanczos on a copy of the random block (V=Bf, Vprev=Cf, W=HX)
-    if (N > 4 * lz_steps) {
+    if (resident && N > 4 * lz_steps) {
+        double ub_factor = 1.03;
+        if (const char* env = getenv("SCB_UBFACTOR")) ub_factor = atof(env) > 1.0 ? atof(env) : ub_factor;
+        SCB_TRY(resident_lanczos(B, n, b, rowptr, w.res, lz_steps, seed ^ 0x9e3779b97f4a7c15ull, ub_factor, w.state, st));
+    } else if (N > 4 * lz_steps) {
         const size_t vec_bytes = sizeof(double) * (size_t)B * N * b;
         SCB_CUDA(cudaMemcpyAsync(w.Bf, w.A, vec_bytes, cudaMemcpyDeviceToDevice, st));
         SCB_CUDA(cudaMemsetAsync(w.Cf, 0, vec_bytes, st));

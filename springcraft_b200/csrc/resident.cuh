@@ -35,6 +35,7 @@ struct ResLayout {         // device buffers of the resident operator (carved fr
     uint16_t* order;       // [B][G*rpw] row pair of (group, slot); 0xFFFF = empty slot
     float* diag32;         // [B][n][12] diagonal blocks (9 used, row-major)
     int32_t* flag;         // [1] != 0: some block is not of the form -v v^T (positive t) -> path unusable
+    double* est;           // [B] Lanczos estimate of the largest eigenvalue
     int G;                 // groups per structure
     int rpw;               // row pairs per group
     int cols;              // block columns per CTA (16, 8 or 4)

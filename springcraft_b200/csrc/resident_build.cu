@@ -21,6 +21,37 @@ __device__ __forceinline__ bool block_to_v(const double* __restrict__ blk, float
     return bad;
 }
 
+
+// cursor over the merged column list of a row pair that stops only at columns of one parity
+struct ParityCursor {
+    int64_t a, ae, b, be;
+    int parity;
+};
+__device__ __forceinline__ void cursor_init(ParityCursor& c, const int64_t* __restrict__ rowptr, int64_t r0, bool has1,
+                                            int parity) {
+    c.a = rowptr[r0]; c.ae = rowptr[r0 + 1];
+    c.b = has1 ? rowptr[r0 + 1] : 0; c.be = has1 ? rowptr[r0 + 2] : 0;
+    c.parity = parity;
+}
+// next merged contact of the cursor's parity -> record; false when the list is exhausted
+__device__ __forceinline__ bool cursor_next(ParityCursor& c, const int32_t* __restrict__ col,
+                                            const double* __restrict__ offdiag, ResRec& e, bool& bad) {
+    while (c.a < c.ae || c.b < c.be) {
+        const int ca = c.a < c.ae ? col[c.a] : 0x7fffffff;
+        const int cb = c.b < c.be ? col[c.b] : 0x7fffffff;
+        const int m = min(ca, cb);
+        if ((m & 1) != c.parity) { c.a += (ca == m); c.b += (cb == m); continue; }
+        e.col = m;
+        e.pad = 0;
+        if (ca == m) { bad |= block_to_v(offdiag + c.a * 9, e.v0); ++c.a; }
+        else { e.v0[0] = e.v0[1] = e.v0[2] = 0.f; }
+        if (cb == m) { bad |= block_to_v(offdiag + c.b * 9, e.v1); ++c.b; }
+        else { e.v1[0] = e.v1[1] = e.v1[2] = 0.f; }
+        return true;
+    }
+    return false;
+}
+
 constexpr int kBuildThreads = 256;
 constexpr int kBuildMaxPairs = 768;
 
@@ -30,6 +61,7 @@ resident_build_kernel(int n, int np, int G, int rpw, int64_t rec_pad, const int6
                       const double* __restrict__ diag, ResRec* __restrict__ rec, int32_t* __restrict__ gstart,
                       uint16_t* __restrict__ order, float* __restrict__ diag32, int32_t* __restrict__ flag) {
     __shared__ int cnt[kBuildMaxPairs];
+    __shared__ int cnt_even[kBuildMaxPairs];
     __shared__ int rnk[kBuildMaxPairs];
     __shared__ int gs[kResMaxWarps + 1];
     __shared__ int bad_any;
@@ -43,7 +75,7 @@ resident_build_kernel(int n, int np, int G, int rpw, int64_t rec_pad, const int6
         const bool has1 = 2 * t + 1 < n;
         int64_t a = rowptr[r0], ae = rowptr[r0 + 1];
         int64_t b = has1 ? rowptr[r0 + 1] : 0, be = has1 ? rowptr[r0 + 2] : 0;
-        int c = 0;
+        int c = 0, ce = 0;
         while (a < ae || b < be) {
             const int ca = a < ae ? col[a] : 0x7fffffff;
             const int cb = b < be ? col[b] : 0x7fffffff;
@@ -51,8 +83,10 @@ resident_build_kernel(int n, int np, int G, int rpw, int64_t rec_pad, const int6
             a += (ca == m);
             b += (cb == m);
             ++c;
+            ce += !(m & 1);
         }
         cnt[t] = c;
+        cnt_even[t] = ce;
     }
     __syncthreads();
     // ---- 2. descending order by count (ties by index): rank by counting
@@ -85,6 +119,62 @@ resident_build_kernel(int n, int np, int G, int rpw, int64_t rec_pad, const int6
     const int64_t start = ((rowptr[row_base] + rec_pad * s) + 7) & ~(int64_t)7;
     ResRec* base = rec + start;
     bool bad = false;
+    ResRec zrec;
+    zrec.col = 0; zrec.pad = 0;
+    zrec.v0[0] = zrec.v0[1] = zrec.v0[2] = 0.f;
+    zrec.v1[0] = zrec.v1[1] = zrec.v1[2] = 0.f;
+    if (rpw == 8) {
+        // 16 columns per CTA: a quarter warp (one shared-memory wavefront of the z gather) serves the row pairs of
+        // slots 2m and 2m+1, and node j sits at bank offset 16 (j mod 2).  Order the two record lists so that, step by
+        // step, the two columns have different parity whenever the lists allow it: the gather is then conflict free.
+        for (int r2 = tid; r2 < G * 4; r2 += kBuildThreads) {
+            const int g = r2 >> 2, m = r2 & 3;
+            const int iters = gs[g + 1] - gs[g];
+            const int rA = g * 8 + 2 * m, rB = rA + 1;
+            const int tA = rA < np ? (int)ord[rA] : -1, tB = rB < np ? (int)ord[rB] : -1;
+            ParityCursor cur[2][2];     // [A|B][even|odd]
+            int rem[2][2] = {{0, 0}, {0, 0}};
+            if (tA >= 0) {
+                cursor_init(cur[0][0], rowptr, row_base + 2 * tA, 2 * tA + 1 < n, 0);
+                cursor_init(cur[0][1], rowptr, row_base + 2 * tA, 2 * tA + 1 < n, 1);
+                rem[0][0] = cnt_even[tA]; rem[0][1] = cnt[tA] - cnt_even[tA];
+            }
+            if (tB >= 0) {
+                cursor_init(cur[1][0], rowptr, row_base + 2 * tB, 2 * tB + 1 < n, 0);
+                cursor_init(cur[1][1], rowptr, row_base + 2 * tB, 2 * tB + 1 < n, 1);
+                rem[1][0] = cnt_even[tB]; rem[1][1] = cnt[tB] - cnt_even[tB];
+            }
+            ResRec* outA = base + (int64_t)gs[g] * 8 + 2 * m;
+            for (int i = 0; i < iters; ++i) {
+                const bool actA = rem[0][0] + rem[0][1] > 0, actB = rem[1][0] + rem[1][1] > 0;
+                int pA, pB;
+                if (actA && actB) {
+                    const bool f1 = rem[0][0] > 0 && rem[1][1] > 0;   // A even, B odd
+                    const bool f2 = rem[0][1] > 0 && rem[1][0] > 0;   // A odd, B even
+                    bool first;
+                    if (f1 && f2) first = (rem[0][0] - rem[0][1]) + (rem[1][1] - rem[1][0]) >= 0;
+                    else first = f1 || !f2;
+                    pA = first ? 0 : 1; pB = first ? 1 : 0;
+                    if (!f1 && !f2) {                                  // forced: same parity on both sides
+                        pA = rem[0][0] > 0 ? 0 : 1;
+                        pB = rem[1][0] > 0 ? 0 : 1;
+                    }
+                } else if (actA) {
+                    pA = rem[0][0] >= rem[0][1] ? 0 : 1; pB = pA ^ 1;
+                } else {
+                    pB = rem[1][0] >= rem[1][1] ? 0 : 1; pA = pB ^ 1;
+                }
+                ResRec e = zrec;
+                e.col = pA;                                            // padding record: harmless column of the free parity
+                if (actA) { cursor_next(cur[0][pA], col, offdiag, e, bad); --rem[0][pA]; }
+                outA[(int64_t)i * 8] = e;
+                e = zrec;
+                e.col = pB;
+                if (actB) { cursor_next(cur[1][pB], col, offdiag, e, bad); --rem[1][pB]; }
+                outA[(int64_t)i * 8 + 1] = e;
+            }
+        }
+    } else
     for (int r = tid; r < G * rpw; r += kBuildThreads) {
         const int g = r / rpw, slot = r % rpw;
         const int iters = gs[g + 1] - gs[g];
@@ -111,11 +201,7 @@ resident_build_kernel(int n, int np, int G, int rpw, int64_t rec_pad, const int6
                 ++i;
             }
         }
-        ResRec z;
-        z.col = 0; z.pad = 0;
-        z.v0[0] = z.v0[1] = z.v0[2] = 0.f;
-        z.v1[0] = z.v1[1] = z.v1[2] = 0.f;
-        for (; i < iters; ++i) out[(int64_t)i * rpw] = z;
+        for (; i < iters; ++i) out[(int64_t)i * rpw] = zrec;
     }
     // ---- 5. diagonal blocks in single precision, 12 floats per node
     for (int q = tid; q < n * 12; q += kBuildThreads) {
