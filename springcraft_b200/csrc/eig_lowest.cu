@@ -17,7 +17,6 @@
 
 namespace scb {
 
-int64_t resident_rec_pad_of(int n, int cols);
 
 constexpr int kLanczosSteps = 8;      // column-wise Lanczos steps of the spectrum-bound estimator (6: +4 % iterations, 10/12: same iterations, 1-3 % slower)
 constexpr int kLanczosStepsMax = 16;  // workspace is sized for this many (SCB_LANCZOS)
@@ -71,8 +70,7 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
     L.cols = (D == 3) ? resident_cols(n, b) : 0;
     if (L.cols > 0) {
         L.rpw = 128 / L.cols;
-        L.G = ((n + 1) / 2 + L.rpw - 1) / L.rpw;
-        L.rec_pad = resident_rec_pad_of(n, L.cols);
+        resident_shape(n, L.cols, &L.G, &L.nsplit, &L.rec_mul, &L.rec_pad);
         L.rec = ar.take<ResRec>(resident_capacity(B, n, P, L.cols));
         L.gstart = ar.take<int32_t>((size_t)B * (L.G + 1));
         L.order = ar.take<uint16_t>((size_t)B * L.G * L.rpw);

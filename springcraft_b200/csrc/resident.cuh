@@ -32,11 +32,13 @@ constexpr int kResDegreeCap = 64;
 struct ResLayout {         // device buffers of the resident operator (carved from the solver workspace)
     ResRec* rec;           // [capacity] interleaved records; structure s starts at rowptr[s*n] + rec_pad*s
     int32_t* gstart;       // [B][G+1] prefix of group iteration counts
-    uint16_t* order;       // [B][G*rpw] row pair of (group, slot); 0xFFFF = empty slot
+    uint16_t* order;       // [B][G*rpw] row pair of (group, slot); 0xFFFF = empty slot; bit 15 = half of a split pair
     float* diag32;         // [B][n][12] diagonal blocks (9 used, row-major)
     int32_t* flag;         // [1] != 0: some block is not of the form -v v^T (positive t) -> path unusable
     double* est;           // [B] Lanczos estimate of the largest eigenvalue
-    int G;                 // groups per structure
+    int G;                 // groups (= warps) per structure
+    int nsplit;            // 16-column layout: the nsplit longest row pairs are split over two slots
+    int rec_mul;           // structure s starts at record rec_mul * rowptr[s*n] + rec_pad * s (rounded up to 8)
     int rpw;               // row pairs per group
     int cols;              // block columns per CTA (16, 8 or 4)
     int64_t rec_pad;       // extra record capacity per structure (padding of the groups)
@@ -44,6 +46,7 @@ struct ResLayout {         // device buffers of the resident operator (carved fr
 
 // columns per CTA for a structure of n nodes (0: does not fit -> streaming kernels)
 int resident_cols(int n, int b);
+void resident_shape(int n, int cols, int* G, int* nsplit, int* rec_mul, int64_t* rec_pad);
 size_t resident_capacity(int B, int n, int64_t P, int cols);
 int resident_build(int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
                    const double* diag, const ResLayout& L, cudaStream_t st);

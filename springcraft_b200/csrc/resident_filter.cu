@@ -45,6 +45,21 @@ __device__ __forceinline__ void rec_apply(const float4 ra, const float4 rb, cons
     }
 }
 
+// split row pairs: add the partial sums of the two slots of a quarter (lanes l and l ^ LPP); warp-uniform call
+template <int LPP>
+__device__ __forceinline__ void merge_split(float2 (&acc)[2][3][2], bool split) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float px = __shfl_xor_sync(0xffffffffu, acc[h][a][u].x, LPP);
+                const float py = __shfl_xor_sync(0xffffffffu, acc[h][a][u].y, LPP);
+                if (split) { acc[h][a][u].x += px; acc[h][a][u].y += py; }
+            }
+}
+
 // warp -> group: the longest groups go to the highest warp ids (issue priority), snaked over the 4 sub-partitions
 __device__ __forceinline__ int warp_group(int warp, int nwarps) {
     const int kq = warp >> 2, smsp = warp & 3;
@@ -99,7 +114,8 @@ struct LaneCtx {
     const float* dg0;      // diagonal block of the first node
     int iters;             // warp iterations of the group
     int i0;                // first node of the row pair
-    int nh;                // nodes owned in this group: 0 (empty slot), 1 (last pair of an odd n) or 2
+    int nh;                // nodes owned in this group: 0 (empty slot / second half of a split pair), 1 (last pair of an odd n) or 2
+    bool split;            // the slot holds half of a split row pair: partial sums are added across the quarter
 };
 
 template <int COLS>
@@ -108,16 +124,18 @@ __device__ __forceinline__ LaneCtx lane_ctx(int g, int G, int slot, int64_t s, i
                                             const uint16_t* __restrict__ order, const float* __restrict__ diag32) {
     constexpr int RPW = 32 / (COLS / 4);
     LaneCtx c;
-    c.rp = nullptr; c.dg0 = diag32; c.iters = 0; c.i0 = 0; c.nh = 0;
+    c.rp = nullptr; c.dg0 = diag32; c.iters = 0; c.i0 = 0; c.nh = 0; c.split = false;
     if (g < 0 || g >= G) return c;
-    const int p = order[s * (int64_t)G * RPW + g * RPW + slot];
+    const int praw = order[s * (int64_t)G * RPW + g * RPW + slot];
     const int g0 = gst[g];
     c.iters = gst[g + 1] - g0;
     c.rp = reinterpret_cast<const float4*>(rec + start + (int64_t)g0 * RPW + slot);
-    if (p != 0xFFFF) {
+    if (praw != 0xFFFF) {
+        const int p = praw & 0x7FFF;
+        c.split = (praw & 0x8000) != 0;
         c.i0 = 2 * p;
-        c.nh = (c.i0 + 1 < n) ? 2 : 1;
         c.dg0 = diag32 + (s * n + c.i0) * 12;
+        if (!c.split || !(slot & 1)) c.nh = (c.i0 + 1 < n) ? 2 : 1;   // the even slot of a split pair owns the rows
     }
     return c;
 }
@@ -138,7 +156,7 @@ __device__ __forceinline__ void warp_groups(int warp, int nwarps, int G, int gpw
 
 template <int COLS, int GPW>
 __global__ void __launch_bounds__(kResMaxWarps * 32, 1)
-resident_filter_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __restrict__ rowptr,
+resident_filter_kernel(int n, int b, int G, int rec_mul, int64_t rec_pad, const int64_t* __restrict__ rowptr,
                        const ResRec* __restrict__ rec, const int32_t* __restrict__ gstart,
                        const uint16_t* __restrict__ order, const float* __restrict__ diag32,
                        const double* X, const double* __restrict__ HX, const double* __restrict__ theta,
@@ -193,12 +211,16 @@ resident_filter_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __re
     const int gc0 = cg * COLS + c0;                   // ... in the block
     const double* Xs = X + s * (int64_t)N * b;
     const double* Hs = HX + s * (int64_t)N * b;
-    const int64_t start = ((rowptr[s * n] + rec_pad * s) + 7) & ~(int64_t)7;
+    const int64_t start = ((rec_mul * rowptr[s * n] + rec_pad * s) + 7) & ~(int64_t)7;
     const int32_t* gst = gstart + s * (int64_t)(G + 1);
 
     LaneCtx ctx[GPW];
+    bool wsplit[GPW];
 #pragma unroll
-    for (int gi = 0; gi < GPW; ++gi) ctx[gi] = lane_ctx<COLS>(gsel[gi], G, slot, s, n, rec, start, gst, order, diag32);
+    for (int gi = 0; gi < GPW; ++gi) {
+        ctx[gi] = lane_ctx<COLS>(gsel[gi], G, slot, s, n, rec, start, gst, order, diag32);
+        wsplit[gi] = __any_sync(0xffffffffu, ctx[gi].split);
+    }
 
     // ---- prologue: residual of the lane's rows -> RH, z_1 -> ZA, z_0 = 0 -> ZB
 #pragma unroll
@@ -237,6 +259,7 @@ resident_filter_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __re
             const LaneCtx c = ctx[gi];
             float2 acc[2][3][2];
             walk_records<COLS>(c.rp, c.iters, stride4, ZA, c0, acc);
+            if (wsplit[gi]) merge_split<LPP>(acc, c.split);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h >= c.nh) break;
@@ -380,7 +403,7 @@ constexpr int kResLanczosMax = 16;
 
 template <int COLS>
 __global__ void __launch_bounds__(kResMaxWarps * 32, 1)
-resident_lanczos_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __restrict__ rowptr,
+resident_lanczos_kernel(int n, int b, int G, int rec_mul, int64_t rec_pad, const int64_t* __restrict__ rowptr,
                         const ResRec* __restrict__ rec, const int32_t* __restrict__ gstart,
                         const uint16_t* __restrict__ order, const float* __restrict__ diag32, int steps,
                         uint64_t seed, double* __restrict__ est) {
@@ -401,12 +424,11 @@ resident_lanczos_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __r
     const int g = warp_group(warp, nwarps);
     const int slot = lane / LPP, q = lane % LPP;
     const int c0 = 4 * q, gc0 = cg * COLS + c0;
-    int p = 0xFFFF;
-    if (g < G) p = order[s * (int64_t)G * RPW + g * RPW + slot];
-    const bool own = p != 0xFFFF;
-    const int i0 = 2 * p;
-    const bool has1 = own && (i0 + 1 < n);
-    const int nh = own ? (has1 ? 2 : 1) : 0;
+    const int64_t start = ((rec_mul * rowptr[s * n] + rec_pad * s) + 7) & ~(int64_t)7;
+    const int32_t* gst = gstart + s * (int64_t)(G + 1);
+    const LaneCtx ctx = lane_ctx<COLS>(g, G, slot, s, n, rec, start, gst, order, diag32);
+    const bool wsplit = __any_sync(0xffffffffu, ctx.split);
+    const int i0 = ctx.i0, nh = ctx.nh;
 
     // random start, normalised per column
     float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -438,17 +460,10 @@ resident_lanczos_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __r
     }
     __syncthreads();
 
-    const int64_t start = ((rowptr[s * n] + rec_pad * s) + 7) & ~(int64_t)7;
-    const int32_t* gst = gstart + s * (int64_t)(G + 1);
-    int iters = 0;
-    const float4* rp = nullptr;
-    if (g < G) {
-        const int g0 = gst[g];
-        iters = gst[g + 1] - g0;
-        rp = reinterpret_cast<const float4*>(rec + start + (int64_t)g0 * RPW + slot);
-    }
     constexpr int stride4 = RPW * 2;
-    const float* dg0 = diag32 + (s * n + (own ? i0 : 0)) * 12;
+    const float4* rp = ctx.rp;
+    const int iters = ctx.iters;
+    const float* dg0 = ctx.dg0;
     float4 bprev = make_float4(0.f, 0.f, 0.f, 0.f);      // beta_{j-1} per column
 
     for (int j = 0; j < steps; ++j) {
@@ -461,6 +476,7 @@ resident_lanczos_kernel(int n, int b, int G, int64_t rec_pad, const int64_t* __r
         if (g < G) {
             float2 acc[2][3][2];
             walk_records<COLS>(rp, iters, stride4, VA, c0, acc);
+            if (wsplit) merge_split<LPP>(acc, ctx.split);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h >= nh) break;
@@ -579,11 +595,13 @@ static int launch_filter(int B, int n, int b, const int64_t* rowptr, const ResLa
     if (gpw == 1) {
         SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resident_filter_kernel<COLS, 1><<<grid, 32 * 4 * ((L.G + 3) / 4), smem, st>>>(
-            n, b, L.G, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz, Xout);
+            n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz,
+            Xout);
     } else {
         SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resident_filter_kernel<COLS, 2><<<grid, 32 * ((L.G + 1) / 2), smem, st>>>(
-            n, b, L.G, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz, Xout);
+            n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz,
+            Xout);
     }
     SCB_LAUNCH_CHECK();
     return SCB_OK;
@@ -596,8 +614,8 @@ static int launch_lanczos(int B, int n, int b, const int64_t* rowptr, const ResL
     const size_t smem = sizeof(float) * ((size_t)3 * 3 * n * COLS + (size_t)nwarps * COLS);
     SCB_CUDA(cudaFuncSetAttribute(resident_lanczos_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(b / COLS), (unsigned)B);
-    resident_lanczos_kernel<COLS><<<grid, 32 * nwarps, smem, st>>>(n, b, L.G, L.rec_pad, rowptr, L.rec, L.gstart,
-                                                                  L.order, L.diag32, steps, seed, L.est);
+    resident_lanczos_kernel<COLS><<<grid, 32 * nwarps, smem, st>>>(n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec,
+                                                                  L.gstart, L.order, L.diag32, steps, seed, L.est);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
