@@ -179,12 +179,18 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         if ((status = deflate(B, N, b, nz, Z, w.A, w.P, nullptr, st)) != SCB_OK) return status;
         for (int outer = 0; outer <= max_outer; ++outer) {
             if ((status = apply(w.A, nullptr, w.HX, nullptr, 0)) != SCB_OK) break;
-            if ((status = gram(B, N, b, w.A, w.A, w.S, done, st)) != SCB_OK) break;
-            if ((status = gram(B, N, b, w.A, w.HX, w.T, done, st)) != SCB_OK) break;
-            if ((status = small_rr(B, b, w.S, w.T, w.theta, w.Cm, done, 1, st)) != SCB_OK) break;
-            if ((status = rotate(B, N, b, w.Cm, w.A, w.A, w.HX, w.HX, done, st)) != SCB_OK) break;
-            if ((status = zero_active_rn2(B, b, w.rn2, done, st)) != SCB_OK) break;
-            if ((status = residual_norms(B, N, b, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
+            if (b == 32) {
+                if ((status = gram2_dmma(B, N, w.A, w.HX, w.S, w.T, done, st)) != SCB_OK) break;
+                if ((status = small_rr(B, b, w.S, w.T, w.theta, w.Cm, done, 1, st)) != SCB_OK) break;
+                if ((status = rotate_resid_dmma(B, N, w.Cm, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
+            } else {
+                if ((status = gram(B, N, b, w.A, w.A, w.S, done, st)) != SCB_OK) break;
+                if ((status = gram(B, N, b, w.A, w.HX, w.T, done, st)) != SCB_OK) break;
+                if ((status = small_rr(B, b, w.S, w.T, w.theta, w.Cm, done, 1, st)) != SCB_OK) break;
+                if ((status = rotate(B, N, b, w.Cm, w.A, w.A, w.HX, w.HX, done, st)) != SCB_OK) break;
+                if ((status = zero_active_rn2(B, b, w.rn2, done, st)) != SCB_OK) break;
+                if ((status = residual_norms(B, N, b, w.A, w.HX, w.theta, w.rn2, done, st)) != SCB_OK) break;
+            }
             if ((status = state_update(B, b, k, tol, w.theta, w.rn2, w.state, w.done, w.n_active, resid, w.skip32,
                                        w.skip64, 0, switch_tol, degree, st)) != SCB_OK)
                 break;

@@ -54,6 +54,12 @@ int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* o
 int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, double* W, const double* alpha,
                  const double* beta_prev, const double* nrm2, cudaStream_t st);
 int lanczos_bound(int B, int b, int k, const double* alpha, const double* beta2, EigState* state, cudaStream_t st);
+// FP64 tensor-core versions for 32-column blocks (tallskinny_dmma.cu): S = X^T X and T = X^T HX in one pass;
+// X <- X C, HX <- HX C fused with the squared residual norms of the rotated pairs
+int gram2_dmma(int B, int64_t N, const double* X, const double* HX, double* S, double* T, const int32_t* done,
+               cudaStream_t st);
+int rotate_resid_dmma(int B, int64_t N, const double* C, double* X, double* HX, const double* theta, double* rn2,
+                      const int32_t* done, cudaStream_t st);
 int gather_results(int B, int b, const double* theta, const EigState* st, double* eigval, int32_t* iters,
                    cudaStream_t s);
 
