@@ -33,16 +33,18 @@ N_RES = 300
 N_CONF = 4096
 K_MODES = 20
 FF_NAME = "TabulatedForceField.e_anm"
+PRECISION = ("fp64 results: Hessian, H X, Rayleigh-Ritz, residuals and the convergence test are FP64; the Chebyshev "
+             "filter acts on the residual-proportional correction only (residual form) and runs in FP32")
 
 
 def make_ensemble(rank, n_conf):
-    """Conformations c = rank*n_conf .. : base chain + N(0, 0.5 A)."""
-    from oracle import enm_oracle as orc  # input generator only (shared with the tests)
-    base = orc.synthetic_chain(N_RES, seed=0)
-    res_name, chain_id, res_id = orc.synthetic_sequence(N_RES, seed=0)
-    rng = np.random.default_rng(1000 + rank)
-    coords = base[None] + rng.normal(0.0, 0.5, size=(n_conf, N_RES, 3))
-    return base, coords, (res_name, chain_id, res_id)
+    """Conformations c = rank*n_conf .. rank*n_conf + n_conf - 1 of the C3 ensemble: base chain +
+    N(0, 0.5 A) drawn with seed 1000 + c -- the same per-conformation generator as the golden fixtures."""
+    from synthetic_inputs import perturbed_conformation, synthetic_chain, synthetic_sequence
+    base = synthetic_chain(N_RES, seed=0)
+    seq = synthetic_sequence(N_RES, seed=0)
+    coords = np.stack([perturbed_conformation(base, rank * n_conf + c, sigma=0.5) for c in range(n_conf)])
+    return base, coords, seq
 
 
 def peaks():
@@ -123,21 +125,23 @@ def _cpu_worker_init():
         pass
 
 
-def time_cpu(coords, seq, n_sample, processes):
-    """structures/s of the CPU reference path on `processes` host cores."""
+def time_cpu(coords, seq, n_sample, processes, return_results=False):
+    """structures/s of the CPU reference path on `processes` host cores (and, on request, what it computed:
+    conformation i % len(coords) -> (eigenvalues 6..25, MSF))."""
     import multiprocessing as mp
     work = [(coords[i % len(coords)], seq) for i in range(n_sample)]
     if processes <= 1:
         t0 = time.perf_counter()
-        for w in work:
-            cpu_structure(w)
-        return n_sample / (time.perf_counter() - t0)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(processes, initializer=_cpu_worker_init) as pool:
-        pool.map(cpu_structure, work[:processes])  # warm the workers (imports, table load)
-        t0 = time.perf_counter()
-        pool.map(cpu_structure, work, chunksize=1)
-        return n_sample / (time.perf_counter() - t0)
+        results = [cpu_structure(w) for w in work]
+        rate = n_sample / (time.perf_counter() - t0)
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(processes, initializer=_cpu_worker_init) as pool:
+            pool.map(cpu_structure, work[:processes])  # warm the workers (imports, table load)
+            t0 = time.perf_counter()
+            results = pool.map(cpu_structure, work, chunksize=1)
+            rate = n_sample / (time.perf_counter() - t0)
+    return (rate, results) if return_results else rate
 
 
 def run_reference(args):
@@ -164,7 +168,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(1),
+        "precision": PRECISION, "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "structures/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -179,17 +183,56 @@ def workload_config(n_gpus):
                     f"{FF_NAME} (13 A cutoff), lowest {K_MODES} non-trivial modes + MSF each",
         "conformations_per_gpu": N_CONF, "residues": N_RES, "force_field": FF_NAME, "modes": K_MODES,
         "tolerance": "residual <= 3e-9 * lambda_20 (eigenvalues ~1e-14, subspace angle ~1e-9, MSF < 1e-8 vs reference)",
+        "precision": PRECISION,
         "parallelism": f"ensemble sharded by conformation over {n_gpus} GPU(s), no data-path collective",
-        "l2_policy": "inputs larger than L2 (per-step working set ~7 GB >> 126 MB)",
+        "l2_policy": "inputs larger than L2 (per-step working set ~5 GB of matrices, records and blocks >> 126 MB)",
     }
 
 
 # ------------------------------------------------------------------ GPU arm
+def dgemm_peak_tflops(torch, n=8192, reps=4):
+    """Live cuBLAS DGEMM throughput: the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry)."""
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def ncu_capture():
+    """DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/roofline_capture.json,
+    written by profiles/extract_roofline.py from the .ncu-rep of the same kernel; carries the commit it was taken at)."""
+    try:
+        with open(join(ROOT, "profiles", "roofline_capture.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+def jittered_grid(n, seed=0, density=0.008):
+    """Fast stand-in for the rejection-sampled cloud of SURVEY 8d at n = 20,000 (the O(n^2) rejection loop takes
+    minutes in Python): grid at the same density, each point jittered by up to a quarter of the pitch."""
+    rng = np.random.default_rng(seed)
+    side = (n / density) ** (1.0 / 3.0)
+    g = int(np.ceil(n ** (1.0 / 3.0)))
+    pts = np.stack(np.meshgrid(*[np.arange(g)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] * (side / g)
+    return pts + rng.uniform(-0.25, 0.25, pts.shape) * (side / g) * 0.5
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     import springcraft_b200 as sc
-    from springcraft_b200 import _lib
+    from springcraft_b200 import _engine, _lib, parallel
     from springcraft_b200._engine import DeviceModel
     from springcraft_b200.ensemble import enm_ensemble_device
 
@@ -201,6 +244,35 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     handle = _lib.require_device()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def timed(fn, steps):
+        barrier()
+        l0 = handle.scb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        return ms, handle.scb_launch_count() - l0, res
+
+    def release():
+        handle.scb_trim_pool()
+        torch.cuda.empty_cache()
+
+    # ================================================================ C3: the metric of record
     base, coords, seq = make_ensemble(rank, N_CONF)
     atoms = sc.AtomArray(base, *seq)
     ff = sc.TabulatedForceField.e_anm(atoms)
@@ -212,34 +284,12 @@ def run_gpu(args):
            torch.empty((N_CONF, N_RES), dtype=torch.float64, device="cuda"),
            torch.empty(N_CONF, dtype=torch.int32, device="cuda"))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step_device():
         return enm_ensemble_device(xyz, ff, k=K_MODES, out=out)
 
     def step_host():
         return sc.enm_ensemble(coords_pinned.numpy(), ff, k=K_MODES,
                                pinned_out=(eig_pinned.numpy(), msf_pinned.numpy(), None))
-
-    def timed(fn, steps):
-        barrier()
-        l0 = handle.scb_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            res = fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = handle.scb_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, res
 
     for _ in range(args.warmup):
         step_device()
@@ -252,102 +302,248 @@ def run_gpu(args):
     for _ in range(min(args.warmup, 2)):
         step_host()
     ms_e2e, _, res_h = timed(step_host, args.steps)
-
-    # sanity: both arms agree, all structures converged
-    assert converged and res_h.converged, "eigensolver did not converge for every conformation"
+    # both arms agree, all structures converged
+    assert converged and res_h.converged and bool(res_h.converged_mask.all()), "eigensolver did not converge for every conformation"
     assert np.allclose(res_h.eigenvalues, eig_d.cpu().numpy(), rtol=1e-9)
     total = N_CONF * world
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+    # ---- roofline of the dominant kernel: the structure-resident filter, timed by the library with CUDA events
+    # around every launch on the launching stream (scb_profile) during one extra, untimed pass
+    roofline = None
+    if rank == 0:
+        import ctypes as C
+        ms_f, n_f, apps = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        handle.scb_profile(1, None, None, None)
+        step_device()
+        torch.cuda.synchronize()
+        handle.scb_profile(0, C.byref(ms_f), C.byref(n_f), C.byref(apps))
+        P_s = n_pairs / N_CONF          # ordered contacts per structure
+        b = 32
+        # SURVEY 8d K3 per operator application and structure, at the precision the kernel computes in (FP32
+        # values: half of the FP64 figure 72(P+n) + 4P + 4(n+1) + 2*8*3n*b): blocks + column indices + row
+        # pointers + block read and written once
+        app_bytes = 36.0 * (P_s + N_RES) + 4.0 * P_s + 4.0 * (N_RES + 1) + 2 * 4.0 * 3 * N_RES * b
+        app_flops = 18.0 * (P_s + N_RES) * b                    # 8d: 3x3-block count
+        rank1_flops = (12.0 * P_s + 18.0 * N_RES) * b           # what the rank-one records actually need
+        sec = ms_f.value * 1e-3
+        pk, pk_kind = peaks()
+        achieved = apps.value * app_bytes / sec / 1e9
+        cap = ncu_capture()
+        roofline = {
+            "bound": "hbm", "kernel": "resident_filter_kernel<16,1> (FP32 residual-form Chebyshev filter, block of one "
+                                      "structure resident in shared memory for all filter steps of an outer iteration)",
+            "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind + " (sustained copy, MEASURED_PEAKS.json)",
+            "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "traffic": None if cap is None else cap.get("dram_bytes_per_launch"),
+            "traffic_source": None if cap is None else {k: cap.get(k) for k in ("file", "commit", "launch", "structures",
+                                                                                "ms", "applications")},
+            "launches": int(n_f.value), "ms_per_launch": ms_f.value / max(1, n_f.value),
+            "structure_applications_per_step": int(apps.value),
+            "bytes_per_launch": apps.value * app_bytes / max(1, n_f.value),
+            "note": "algorithmic bytes = SURVEY 8d per-application figure x (structure x application) units of the launch: "
+                    "what a streaming SpMM would move per application.  The kernel reads the records from L2 and keeps "
+                    "the block in shared memory, so its DRAM traffic is far below that; its real limit is the L1/shared "
+                    "data pipe (ncu: l1tex data-pipe 86 %, FP32 FMA pipe 46 %)",
+            "fp32_tflops_8d_count": apps.value * app_flops / sec / 1e12,
+            "fp32_tflops_rank1_count": apps.value * rank1_flops / sec / 1e12,
+            "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+        }
 
-    # ---- roofline of the dominant kernel (BSR SpMM), timed live with CUDA events
-    model = DeviceModel(coords[:N_CONF], ff, 3)
-    b = 32
-    X = torch.randn((N_CONF, 3 * N_RES, b), dtype=torch.float64, device="cuda")
-    Y = torch.empty_like(X)
-    for _ in range(3):
-        model.spmm_paired(X, Y)
-    reps = 20
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        model.spmm_paired(X, Y)
-    e1.record()
-    torch.cuda.synchronize()
-    spmm_ms = e0.elapsed_time(e1) / reps
-    P, n = model.P, N_RES
-    # 72(P+n) + 4P + 8(n+1) [int64 rowptr] + 2*8*3n*b bytes per application, per batch
-    alg_bytes = 72.0 * (P + N_CONF * n) + 4.0 * P + 8.0 * (N_CONF * n + 1) + 2 * 8.0 * 3 * n * b * N_CONF
-    alg_flops = 18.0 * (P + N_CONF * n) * b
-    pk, pk_kind = peaks()
-    achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "spmm_paired_kernel<3> (row-paired BSR 6x3 x 32-column block)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r1h)
-                "traffic": 7.415e9, "ms_per_launch": spmm_ms, "bytes_per_launch": alg_bytes,
-                "fp64_gflops": alg_flops / (spmm_ms * 1e-3) / 1e9}
+    # ---- CPU baseline beside it (bounded sample, rank 0 only) + parity of the bench's own inputs: the CPU leg's
+    # eigenvalues / MSF of conformations 0..n_sample-1 against the GPU results for the same conformations
+    cpu = None
+    parity = None
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        n_sample = max(cores * 2, 32)
+        cpu_v, cpu_res = time_cpu(coords, seq, n_sample, cores, return_results=True)
+        eig_g, msf_g = eig_d.cpu().numpy(), msf_d.cpu().numpy()
+        eig_c = np.stack([r[0] for r in cpu_res])
+        msf_c = np.stack([r[1] for r in cpu_res])
+        eig_err = float(np.max(np.abs(eig_g[:n_sample] / eig_c - 1.0)))
+        msf_err = float(np.max(np.abs(msf_g[:n_sample] / msf_c - 1.0)))
+        parity = {"structures": n_sample, "eigenvalue_rel_max": eig_err, "msf_rel_max": msf_err,
+                  "tolerance": 1e-8, "ok": bool(eig_err <= 1e-8 and msf_err <= 1e-8),
+                  "against": "CPU reference path (oracle port: dense Hessian + np.linalg.eigh + MSF) on the same conformations"}
+        assert parity["ok"], f"bench inputs: GPU vs CPU reference path mismatch {parity}"
+        cpu = {"value": cpu_v, "unit": "structures/s", "cores": cores, "kind": "port",
+               "sample": f"{n_sample} conformations of the same ensemble, {cores} worker processes, "
+                         "dense Hessian + full np.linalg.eigh + MSF (reference algorithm)"}
 
-    # ---- CPU baseline beside it (bounded sample, rank 0 only)
-    cores = os.cpu_count() or 1
-    n_sample = max(cores * 2, 32)
-    cpu_v = time_cpu(coords, seq, n_sample, cores)
-
-    # ---- secondary: one 20,000-residue structure (north_star target: < 1 s on one B200)
-    large = {}
-    try:
-        from oracle import enm_oracle as orc
-        n_big = 20000
-        big = orc.synthetic_chain(n_big, seed=0)
-        for name, bff in (("InvariantForceField(13)", sc.InvariantForceField(13.0)),
-                          ("TabulatedForceField.e_anm", sc.TabulatedForceField.e_anm(
-                              sc.AtomArray(big, *orc.synthetic_sequence(n_big, seed=0))))):
-            best = None
-            for _ in range(3):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                mb = DeviceModel(big, bff, 3)
-                lam_b, X_b, res_b, it_b, _ = mb.eig_lowest(20, max_outer=400)
-                msf_b = torch.empty((1, n_big), dtype=torch.float64, device="cuda")
-                _lib.check(handle.scb_msf_cols(3, 1, n_big, 32, 0, 20, _lib.ptr(lam_b), _lib.ptr(X_b), 1.0,
-                                               _lib.ptr(msf_b), _lib.stream_ptr()))
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                best = dt if best is None else min(best, dt)
-            large[name] = {"residues": n_big, "ordered_pairs": int(mb.P), "seconds": best,
-                           "outer_iterations": int(it_b[0]), "includes": "H2D of coordinates, contacts, assembly, "
-                           "lowest 20 non-trivial modes, MSF (wall clock, best of 3)"}
-    except Exception as exc:  # secondary information only
-        large = {"error": repr(exc)}
-
+    solver = {"outer_iterations_mean": float(iters_d.abs().double().mean().item()),
+              "outer_iterations_max": int(iters_d.abs().max().item()),
+              "filter_degree": int(os.environ.get("SCB_DEGREE", 32)), "block": 32, "ordered_pairs": int(n_pairs)}
     value = total * args.steps / (ms_dev * 1e-3)
     e2e_v = total * args.steps / (ms_e2e * 1e-3)
-    line = {
-        "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e_v, "unit": "structures/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(coords_pinned.numel() * 8),
-                "d2h_bytes_per_step": int((eig_pinned.numel() + msf_pinned.numel()) * 8)},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": "structures/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} conformations of the same ensemble, {cores} worker processes, "
-                                   "dense Hessian + full np.linalg.eigh + MSF (reference algorithm)"},
-        "single_structure_20k": large,
-        "solver": {"outer_iterations_mean": float(iters_d.abs().double().mean().item()),
-                   "outer_iterations_max": int(iters_d.abs().max().item()), "filter_degree": int(os.environ.get("SCB_DEGREE", 32)),
-                   "block": 32, "ordered_pairs": int(n_pairs)},
-    }
-    print(json.dumps(line))
+    h2d = int(coords_pinned.numel() * 8)
+    d2h = int((eig_pinned.numel() + msf_pinned.numel()) * 8 + N_CONF * 4)
+
+    # ================================================================ the other named shapes
+    extras = {}
+    if not args.no_extras:
+        # ---- C3 strong scaling: BASELINE config[2] is 4,096 conformations in TOTAL, sharded over the GPUs
+        if world > 1:
+            a0, a1 = parallel.shard_range(N_CONF, rank, world)
+            xyz_s = xyz[: a1 - a0].contiguous()
+            out_s = tuple(t[: a1 - a0] for t in out)
+            f_s = lambda: enm_ensemble_device(xyz_s, ff, k=K_MODES, out=out_s)  # noqa: E731
+            f_s()
+            ms_s, _, _ = timed(f_s, args.steps)
+            extras["c3_strong"] = {"conformations_total": N_CONF, "per_gpu": a1 - a0, "ms_per_step": ms_s / args.steps,
+                                   "structures_per_s": N_CONF * args.steps / (ms_s * 1e-3)}
+        del xyz, out, coords_pinned, eig_pinned, msf_pinned
+        release()
+        dgemm = dgemm_peak_tflops(torch)
+        extras["fp64_dgemm_tflops"] = {"value": dgemm, "how": "torch.matmul fp64 8192^3 (cuBLAS), best of 4, CUDA events"}
+        from synthetic_inputs import synthetic_chain, synthetic_sequence
+        if rank == 0:
+            # ---- secondary: one 20,000-residue structure, sparse (north_star target: < 1 s on one B200)
+            large = {}
+            n_big = 20000
+            big = synthetic_chain(n_big, seed=0)
+            for name, bff in (("InvariantForceField(13)", sc.InvariantForceField(13.0)),
+                              ("TabulatedForceField.e_anm", sc.TabulatedForceField.e_anm(
+                                  sc.AtomArray(big, *synthetic_sequence(n_big, seed=0))))):
+                best = None
+                for _ in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    mb = DeviceModel(big, bff, 3)
+                    lam_b, X_b, res_b, it_b, _ = mb.eig_lowest(20, max_outer=400)
+                    msf_b = torch.empty((1, n_big), dtype=torch.float64, device="cuda")
+                    _lib.check(handle.scb_msf_cols(3, 1, n_big, 32, 0, 20, _lib.ptr(lam_b), _lib.ptr(X_b), 1.0,
+                                                   _lib.ptr(msf_b), _lib.stream_ptr()))
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                large[name] = {"residues": n_big, "ordered_pairs": int(mb.P), "seconds": best,
+                               "outer_iterations": int(it_b[0]), "includes": "H2D of coordinates, contacts, assembly, "
+                               "lowest 20 non-trivial modes, MSF (wall clock, best of 3)"}
+                del mb, lam_b, X_b
+            extras["single_structure_20k"] = large
+            # ---- C2: ANM, 1,000-residue chain, HinsenForceField all pairs, full spectrum + MSF + B-factor
+            n2 = 1000
+            c2 = synthetic_chain(n2, seed=0)
+            anm2 = sc.ANM(c2, sc.HinsenForceField())
+            dense = anm2._model_device().dense()
+            _engine.eig_full_dense(dense.clone())
+            best = None
+            for _ in range(3):
+                A = dense.clone()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _engine.eig_full_dense(A)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            N2 = 3 * n2
+            t0 = time.perf_counter()
+            fresh = sc.ANM(c2, sc.HinsenForceField())
+            msf2 = fresh.mean_square_fluctuation()
+            bf2 = fresh.bfactor()
+            api_s = time.perf_counter() - t0
+            flops = 10.0 / 3.0 * N2 ** 3
+            extras["c2_full_spectrum"] = {
+                "residues": n2, "N": N2, "eig_full_seconds": best * 1e-3, "flops_8d": flops,
+                "tflops": flops / (best * 1e-3) / 1e12, "frac_of_dgemm": flops / (best * 1e-3) / 1e12 / dgemm,
+                "api_seconds_hessian_msf_bfactor": api_s, "msf_finite": bool(np.isfinite(msf2).all() and np.isfinite(bf2).all())}
+            del dense, anm2, fresh
+            release()
+        # ---- C5: DCC + linear response on 10,000 residues from 500 modes, row-partitioned over the ranks
+        n5, m5 = 10000, 500
+        gen = torch.Generator("cuda").manual_seed(0)
+        V = torch.linalg.qr(torch.randn((3 * n5, m5), dtype=torch.float64, device="cuda", generator=gen)).Q
+        modes5 = V.T.contiguous()
+        lam5 = torch.sort(torch.rand(m5, dtype=torch.float64, device="cuda", generator=gen) * 9.9 + 0.1).values
+        if world > 1:
+            dist.broadcast(modes5, src=0)
+            dist.broadcast(lam5, src=0)
+        del V
+        c5 = {"residues": n5, "modes": m5, "ranks": world, "operands": "synthetic: V = qr(randn(N,500)), lambda = sort(U(0.1,10)) (SURVEY 8d)"}
+        for D, key in ((3, "anm"), (1, "gnm")):
+            md = modes5 if D == 3 else modes5[:, :n5].contiguous()
+            f5 = lambda: parallel.dcc_row_partitioned(D, lam5, md, norm=True)  # noqa: E731
+            row0, row1, slab = f5()
+            diag = torch.diagonal(slab[:, row0:row1])
+            assert torch.allclose(diag, torch.ones_like(diag), atol=1e-12), "normalised DCC diagonal"
+            ms5 = min(timed(f5, 1)[0] for _ in range(3))
+            fl = 2.0 * n5 * n5 * D * m5
+            c5[key] = {"ms": ms5, "tflops_aggregate": fl / (ms5 * 1e-3) / 1e12,
+                       "frac_of_dgemm": fl / (ms5 * 1e-3) / 1e12 / (dgemm * world), "rows_per_rank": row1 - row0}
+            del slab
+        force = torch.zeros(3 * n5, dtype=torch.float64, device="cuda")
+        force[3 * 42] = 1.0
+        _engine.modes_linear_response(lam5, modes5, force)
+        ms_lr = min(timed(lambda: _engine.modes_linear_response(lam5, modes5, force), 1)[0] for _ in range(3))
+        c5["linear_response"] = {"ms": ms_lr, "gb_s": 2 * 8.0 * 3 * n5 * m5 / (ms_lr * 1e-3) / 1e9,
+                                 "frac_of_hbm": 2 * 8.0 * 3 * n5 * m5 / (ms_lr * 1e-3) / 1e9 / peaks()[0]["hbm_gbs"],
+                                 "note": "two passes over the 120 MB mode matrix (8Nm bytes each); replicated per rank"}
+        extras["c5_dcc"] = c5
+        del modes5, lam5
+        release()
+        # ---- C4: 20,000 residues, ParameterFreeForceField all pairs (60k x 60k fp64), lowest 100 modes, row slabs
+        if not args.skip_c4:
+            from springcraft_b200.dense_solver import DenseRowOperator, eig_lowest_dense
+            n4, k4 = 20000, 100
+            c4xyz = jittered_grid(n4, seed=0)
+            barrier()
+            t0 = time.perf_counter()
+            op = DenseRowOperator(c4xyz, sc.ParameterFreeForceField(), 3)
+            barrier()
+            t_asm = time.perf_counter() - t0
+            b4 = 128
+            X4 = torch.randn((3 * n4, b4), dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.broadcast(X4, src=0)
+            op.apply(X4)
+            ms_app = timed(lambda: op.apply(X4), 3)[0] / 3
+            Z4 = op.rigid_basis()
+            barrier()
+            t0 = time.perf_counter()
+            theta4, A4, res4, it4 = eig_lowest_dense(op, k4, Z=Z4)
+            barrier()
+            t_solve = time.perf_counter() - t0
+            fl4 = 2.0 * (3 * n4) ** 2 * b4
+            extras["c4_dense"] = {
+                "residues": n4, "modes": k4, "ranks": world, "exchange": op.exchange if world > 1 else "none",
+                "coordinates": "jittered grid at 0.008 atoms/A^3 (fast stand-in for the rejection-sampled cloud)",
+                "assembly_seconds": t_asm, "slab_gb_per_rank": op.slab.numel() * 8 / 1e9, "block": b4,
+                "ms_per_application": ms_app, "tflops_aggregate": fl4 / (ms_app * 1e-3) / 1e12,
+                "frac_of_dgemm": fl4 / (ms_app * 1e-3) / 1e12 / (dgemm * world),
+                "solve_seconds": t_solve, "outer_iterations": int(it4),
+                "max_residual_over_lambda_k": float((res4[:k4].max() / theta4[k4 - 1]).item())}
+            op.close()
+            del op, X4, A4, Z4
+            release()
+        # ---- the partitioned paths against one rank / the golden fixtures (what GPUTEST skips on a 1-GPU lease)
+        if world > 1:
+            from tests.multigpu_checks import run_checks
+            rep = run_checks()
+            extras["multigpu_parity"] = "ok"
+            extras["multigpu_parity_report"] = rep
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "precision": PRECISION, "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_v, "unit": "structures/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "parity_check": parity,
+            "solver": solver,
+        }
+        line.update(extras)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
-
 
 def main():
     ap = argparse.ArgumentParser()
@@ -355,6 +551,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="C3 only: skip C2/C4/C5, strong scaling and the multi-GPU checks")
+    ap.add_argument("--skip-c4", action="store_true", help="skip the 20,000-residue dense all-pairs configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -14,7 +14,8 @@
  *   - unless the name ends in _host, every pointer is a DEVICE pointer owned by
  *     the caller and `stream` is a cudaStream_t passed as void*.  Functions are
  *     asynchronous with respect to the host unless documented otherwise.
- *   - no hidden global state: re-entrant per stream.
+ *   - re-entrant per stream; the only process-wide state is the launch counter, the last-error text and the
+ *     private scratch pool of the whole-path entry points (scb_trim_pool).
  *   - B = number of structures in the batch (ensemble), n = nodes per structure,
  *     D = 1 (GNM / Kirchhoff) or 3 (ANM / Hessian), N = D*n,
  *     P = number of ORDERED contact pairs of the whole batch.
@@ -94,6 +95,11 @@ const char *scb_status_string(int status);
 const char *scb_last_cuda_error(void);
 /* number of kernels this library has launched in this process (bench accounting) */
 uint64_t scb_launch_count(void);
+/* Instrumentation for bench.py (single host thread): while enabled, scb_eig_lowest brackets every launch of the
+ * structure-resident filter kernel with CUDA events on its stream.  Each call returns and resets the accumulated
+ * device time (ms), the number of filter launches and the number of (structure x operator application) units
+ * they processed; enable = 1 / 0 switches the instrumentation, a negative value leaves it unchanged. */
+int scb_profile(int enable, double *filter_ms, int64_t *filter_launches, int64_t *filter_applications);
 
 /* ---------------------------------------------------------------------------
  * K1  contact search.   Replaces interaction.py:149-178 (+ biotite CellList,
@@ -302,11 +308,16 @@ int scb_enm_ensemble(int D, const double *xyz, int B, int n, const scb_ff_desc *
                      int64_t *n_pairs_out, void *stream);
 /* AoS (n,3) -> SoA [3][n] per structure (struc.coord layout -> kernel layout) */
 int scb_coords_to_soa(const double *coord_aos, int B, int n, double *xyz_soa, void *stream);
+/* iters_host[B] (may be NULL): outer iterations per structure, NEGATIVE for a structure that did not converge
+ * (the call then returns SCB_ERR_NOT_CONVERGED and its rows hold the last iterate). */
 int scb_enm_ensemble_host(int D, const double *coord_host, int B, int n,
                           const scb_ff_desc *ff, const scb_patch *patch,
                           const double *masses_dev, int k, double tol,
                           double *eigval_host, double *msf_host, double *modes_host,
-                          int64_t *n_pairs_out, void *stream);
+                          int32_t *iters_host, int64_t *n_pairs_out, void *stream);
+/* The whole-path entry points take their scratch from a library-private memory pool per device that keeps freed
+ * blocks cached between calls; this hands the cached blocks back to the driver (host-synchronous). */
+int scb_trim_pool(void);
 
 #ifdef __cplusplus
 }

@@ -222,6 +222,16 @@ def _fc_base(spec, pairs, sq):
     if spec.kind == "pfree":              # forcefield.py:361-362
         return 1 / sq
     if spec.kind == "tabulated":          # forcefield.py:497-533
+        dense = spec.extra.get("dense_table")
+        if dense is not None:
+            # interaction_matrix edited by the caller (forcefield.py:429-434): the explicit (n,n,k) float32 table
+            if dense.shape[-1] == 1:      # forcefield.py:516-518
+                return dense[i, j, 0]
+            b = np.searchsorted(spec.edges ** 2, sq, side="left")
+            if (b >= len(spec.edges)).any():
+                raise ValueError("Atom interactions above cutoff distance are "
+                                 "not allowed in TabulatedForceField")
+            return dense[i, j, b]
         if spec.edges is None or len(spec.edges) == 1:
             b = np.zeros(len(sq), dtype=np.int64)
         else:
@@ -402,6 +412,15 @@ def linear_response(cov, force):
     return np.dot(cov, np.asarray(force, dtype=float).reshape(-1)).reshape(n, 3)
 
 
+def linear_response_modes(lam, modes, force, mode_subset):
+    """Low-rank linear response "from m modes" (BASELINE config C5): the pseudo-inverse of nma.py:473 restricted
+    to the given non-trivial modes, V_S^T (L_S^-1 (V_S f))."""
+    sub = np.asarray(mode_subset)
+    n = modes.shape[1] // 3
+    f = np.asarray(force, dtype=float).reshape(-1)
+    return (modes[sub].T @ ((modes[sub] @ f) / lam[sub])).reshape(n, 3)
+
+
 def prs(cov, norm=True):
     """nma.py:511-531."""
     n = cov.shape[0] // 3
@@ -420,47 +439,13 @@ def effector_sensor(prs_matrix):
 
 
 # --------------------------------------------------------------------------
-# synthetic inputs -- shared by tests and bench
+# synthetic inputs live in the neutral module synthetic_inputs.py (the GPU arm of
+# bench.py must not import the oracle); re-exported here for the tests and the golden generator
 # --------------------------------------------------------------------------
-def synthetic_chain(n, seed=0, jitter=0.25):
-    """Boustrophedon CA chain: 3.8 A steps along x, 6.0 A row/layer pitch."""
-    nx = int(np.ceil((n * 36.0 / 3.8 ** 2) ** (1.0 / 3.0)))
-    ny = int(np.ceil(np.sqrt(n / nx)))
-    pts = np.zeros((n, 3))
-    for k in range(n):
-        iz, rem = divmod(k, nx * ny)
-        iy, ix = divmod(rem, nx)
-        if iy % 2 == 1:
-            ix = nx - 1 - ix
-        if iz % 2 == 1:
-            iy = ny - 1 - iy
-        pts[k] = (3.8 * ix, 6.0 * iy, 6.0 * iz)
-    rng = np.random.default_rng(seed)
-    return pts + rng.normal(0.0, jitter, size=(n, 3))
+import sys  # noqa: E402
 
-
-def synthetic_sequence(n, seed=0):
-    rng = np.random.default_rng(seed)
-    res_name = np.array(AA_ORDER)[rng.integers(0, 20, size=n)]
-    return res_name, np.full(n, "A"), np.arange(1, n + 1)
-
-
-def synthetic_cloud(n, seed=0, density=0.008, min_dist=3.0):
-    """Uniform cloud at `density` atoms/A^3 with a minimum pair distance."""
-    rng = np.random.default_rng(seed)
-    side = (n / density) ** (1.0 / 3.0)
-    pts = np.zeros((0, 3))
-    while len(pts) < n:
-        cand = rng.random((n, 3)) * side
-        for c in cand:
-            if len(pts) == 0 or np.min(((pts - c) ** 2).sum(1)) >= min_dist ** 2:
-                pts = np.vstack([pts, c])
-                if len(pts) == n:
-                    break
-    return pts
-
-
-def perturbed_conformation(base, c, sigma=0.5):
-    """C3 ensemble member c: base + N(0, sigma) with seed 1000+c."""
-    rng = np.random.default_rng(1000 + c)
-    return base + rng.normal(0.0, sigma, size=base.shape)
+_ROOT = dirname(dirname(realpath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+from synthetic_inputs import (perturbed_conformation, synthetic_chain, synthetic_cloud,  # noqa: E402,F401
+                              synthetic_sequence)

@@ -37,22 +37,23 @@ def _patch_struct(ff, n, keep):
     p = _lib.Patch()
     if shutdown is not None:
         dead = np.zeros(n, dtype=np.uint8)
-        dead[np.asarray(shutdown, dtype=np.int64)] = 1
+        sd = np.asarray(shutdown)
+        # NumPy indexing semantics of the reference (interaction.py:201-203): a boolean mask selects atoms,
+        # integers may be negative
+        dead[sd if sd.dtype == bool else sd.astype(np.int64)] = 1
         t = _lib.to_device(dead, torch.uint8)
         keep.append(t)
         p.dead = t.data_ptr()
     if off is not None:
-        a = np.asarray(off, dtype=np.int64).reshape(-1, 2)
-        _bounds(a, n)
+        a = _bounds(np.asarray(off, dtype=np.int64).reshape(-1, 2), n)
         t = _lib.to_device(a.astype(np.int32), torch.int32)
         keep.append(t)
         p.pair_off = t.data_ptr()
         p.n_pair_off = len(a)
     if on is not None:
-        a = np.asarray(on, dtype=np.int64).reshape(-1, 2)
+        a = _bounds(np.asarray(on, dtype=np.int64).reshape(-1, 2), n)
         if (a[:, 0] == a[:, 1]).any():  # interaction.py:210-211
             raise ValueError("Cannot turn on interaction of an atom with itself")
-        _bounds(a, n)
         t = _lib.to_device(a.astype(np.int32), torch.int32)
         keep.append(t)
         p.pair_on = t.data_ptr()
@@ -61,8 +62,11 @@ def _patch_struct(ff, n, keep):
 
 
 def _bounds(idx, n):
+    """Bounds check with NumPy's semantics; negative indices are normalised (the kernels compare node numbers)."""
     if idx.size and (idx.max() >= n or idx.min() < -n):
-        raise IndexError(f"index {int(idx.max())} is out of bounds for axis 0 with size {n}")
+        bad = int(idx.max()) if idx.max() >= n else int(idx.min())
+        raise IndexError(f"index {bad} is out of bounds for axis 0 with size {n}")
+    return np.where(idx < 0, idx + n, idx)
 
 
 class DeviceModel:

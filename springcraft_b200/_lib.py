@@ -67,6 +67,7 @@ SIGNATURES = {
     "scb_status_string": (C.c_char_p, [_I]),
     "scb_last_cuda_error": (C.c_char_p, []),
     "scb_launch_count": (_U64, []),
+    "scb_profile": (_I, [_I, C.POINTER(_D), C.POINTER(_I64), C.POINTER(_I64)]),
     "scb_contacts_count": (_I, [_P, _I, _I, _D, C.POINTER(Patch), _I, _P, _P]),
     "scb_scan_scratch_bytes": (_SZ, [_I64]),
     "scb_contacts_scan": (_I, [_P, _I64, _P, _P, _P]),
@@ -116,7 +117,8 @@ SIGNATURES = {
                               _P, _P, _P, _P, C.POINTER(_I64), _P]),
     "scb_coords_to_soa": (_I, [_P, _I, _I, _P, _P]),
     "scb_enm_ensemble_host": (_I, [_I, _P, _I, _I, C.POINTER(FFDesc), C.POINTER(Patch), _P, _I, _D,
-                                   _P, _P, _P, C.POINTER(_I64), _P]),
+                                   _P, _P, _P, _P, C.POINTER(_I64), _P]),
+    "scb_trim_pool": (_I, []),
 }
 
 _lib = None

@@ -23,8 +23,8 @@ class ANM(ENMBase):
     def normal_mode(self, index, amplitude, frames, movement="sine"):
         return nma.normal_mode(self, index, amplitude, frames, movement)
 
-    def linear_response(self, force):
-        return nma.linear_response(self, force)
+    def linear_response(self, force, *, mode_subset=None):
+        return nma.linear_response(self, force, mode_subset=mode_subset)
 
     def prs_effector_sensor(self, norm=True):
         prs_mat = nma.prs(self, norm)

@@ -1,7 +1,7 @@
 // status strings / error bookkeeping of the C ABI
 #include <string.h>
 
-#include "common.cuh"
+#include "resident.cuh"
 
 namespace scb {
 static thread_local char g_last_error[512] = "";
@@ -12,7 +12,29 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line) {
 }
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+static int g_profile_on = 0;
+static double g_prof_ms = 0.0;
+static long long g_prof_launches = 0;
+static unsigned long long g_prof_apps = 0;
+bool profile_enabled() { return __atomic_load_n(&g_profile_on, __ATOMIC_RELAXED) != 0; }
+void profile_add(double filter_ms, long long launches, unsigned long long applications) {
+    g_prof_ms += filter_ms;
+    g_prof_launches += launches;
+    g_prof_apps += applications;
+}
 }  // namespace scb
+
+extern "C" int scb_profile(int enable, double* filter_ms, int64_t* filter_launches, int64_t* filter_applications) {
+    if (filter_ms) *filter_ms = scb::g_prof_ms;
+    if (filter_launches) *filter_launches = scb::g_prof_launches;
+    if (filter_applications) *filter_applications = (int64_t)scb::g_prof_apps;
+    scb::g_prof_ms = 0.0;
+    scb::g_prof_launches = 0;
+    scb::g_prof_apps = 0;
+    if (enable >= 0) __atomic_store_n(&scb::g_profile_on, enable != 0, __ATOMIC_RELAXED);
+    return SCB_OK;
+}
 
 extern "C" uint64_t scb_launch_count(void) { return __atomic_load_n(&scb::g_launches, __ATOMIC_RELAXED); }
 

@@ -77,6 +77,7 @@ static size_t carve(Arena& ar, EigWork* w, int D, int B, int n, int b, int nz, i
         L.diag32 = ar.take<float>((size_t)B * n * 12);
         L.flag = ar.take<int32_t>(1);
         L.est = ar.take<double>(B);
+        L.app_counter = ar.take<unsigned long long>(1);
     }
     return ar.off;
 }
@@ -177,6 +178,12 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
         // deflated block X + |r| z.  The corrected block is nearly orthonormal (z ~ the error of X), so no
         // separate orthonormalisation pass is needed: the Cholesky factor of X^T X inside rr_kernel does it.
         if ((status = deflate(B, N, b, nz, Z, w.A, w.P, nullptr, st)) != SCB_OK) return status;
+        const bool prof = profile_enabled();
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        double prof_ms = 0.0;
+        long long prof_launches = 0;
+        SCB_CUDA(cudaMemsetAsync(w.res.app_counter, 0, sizeof(unsigned long long), st));
+        if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); }
         for (int outer = 0; outer <= max_outer; ++outer) {
             if ((status = apply(w.A, nullptr, w.HX, nullptr, 0)) != SCB_OK) break;
             if (b == 32) {
@@ -201,9 +208,27 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
                 break;
             }
             if (*h_active == 0 || outer == max_outer) break;
+            if (prof) cudaEventRecord(ev0, st);
             if ((status = resident_filter(B, n, b, rowptr, w.res, w.A, w.HX, w.theta, w.rn2, w.state, done, Z, nz,
                                           w.A, st)) != SCB_OK)
                 break;
+            if (prof) {   // scb_profile: device time of the filter launches (the stream is synchronised once per
+                          // outer iteration anyway; the extra synchronisation only exists while profiling)
+                cudaEventRecord(ev1, st);
+                cudaEventSynchronize(ev1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev0, ev1);
+                prof_ms += ms;
+                ++prof_launches;
+            }
+        }
+        if (prof) {
+            unsigned long long apps = 0;
+            cudaMemcpyAsync(&apps, w.res.app_counter, sizeof(apps), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            profile_add(prof_ms, prof_launches, apps);
+            cudaEventDestroy(ev0);
+            cudaEventDestroy(ev1);
         }
         if (status != SCB_OK) return status;
         SCB_TRY(gather_results(B, b, w.theta, w.state, eigval, iters, st));

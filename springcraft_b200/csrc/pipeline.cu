@@ -4,6 +4,8 @@
 // (anm.py:62-148 + nma.py:29-184), with H2D/D2H inside.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "subspace.cuh"
 
 namespace scb {
@@ -39,27 +41,42 @@ __global__ void slice_eigval_kernel(int B, int b, int k0, int k, const double* _
     out[q] = theta[(int64_t)(q / k) * b + k0 + q % k];
 }
 
-static void configure_pool_once() {
-    static bool done = false;
-    if (done) return;
+// Scratch of the whole-path entry points comes from a PRIVATE memory pool per device (created on first use,
+// guarded by a mutex): its release threshold keeps the blocks cached between calls without touching the default
+// pool that the caller's allocator (PyTorch) uses.  scb_trim_pool() hands the cached blocks back to the driver.
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+
+static cudaMemPool_t device_pool() {
     int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        g_pools[dev] = pool;
     }
-    done = true;
+    return g_pools[dev];
 }
 
 struct Scratch {
     cudaStream_t st;
+    cudaMemPool_t pool;
     void* ptrs[24];
     int count = 0;
-    explicit Scratch(cudaStream_t s) : st(s) {}
+    explicit Scratch(cudaStream_t s) : st(s), pool(device_pool()) {}
     template <typename T>
     int alloc(T** p, size_t elems) {
         void* v = nullptr;
-        cudaError_t e = cudaMallocAsync(&v, elems * sizeof(T) + 256, st);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&v, elems * sizeof(T) + 256, pool, st)
+                             : cudaMallocAsync(&v, elems * sizeof(T) + 256, st);
         if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return SCB_ERR_CUDA; }
         ptrs[count++] = v;
         *p = static_cast<T*>(v);
@@ -76,6 +93,14 @@ struct Scratch {
 
 using namespace scb;
 
+extern "C" int scb_trim_pool(void) {
+    cudaMemPool_t pool = device_pool();
+    if (!pool) return SCB_OK;
+    SCB_CUDA(cudaDeviceSynchronize());
+    SCB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return SCB_OK;
+}
+
 extern "C" int scb_coords_to_soa(const double* coord_aos, int B, int n, double* xyz_soa, void* stream) {
     if (!coord_aos || !xyz_soa || B < 1 || n < 1) return SCB_ERR_INVALID;
     const int64_t total = (int64_t)B * n;
@@ -90,7 +115,6 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
     if (!xyz || !ff || !eigval || !msf || B < 1 || n < 1 || k < 1 || (D != 1 && D != 3)) return SCB_ERR_INVALID;
     if (ff->cutoff_sq < 0.0) return SCB_ERR_UNSUPPORTED;  // all-pairs force fields: dense slab path
     if (B > 65535) return SCB_ERR_UNSUPPORTED;   // structures are indexed by blockIdx.y: callers chunk larger batches
-    configure_pool_once();
     cudaStream_t st = as_stream(stream);
     const int nz = (D == 3) ? 6 : 1;
     const int b = (k + 8 <= 32) ? 32 : 64;
@@ -174,13 +198,14 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
 extern "C" int scb_enm_ensemble_host(int D, const double* coord_host, int B, int n, const scb_ff_desc* ff,
                                      const scb_patch* patch, const double* masses_dev, int k, double tol,
                                      double* eigval_host, double* msf_host, double* modes_host,
-                                     int64_t* n_pairs_out, void* stream) {
+                                     int32_t* iters_host, int64_t* n_pairs_out, void* stream) {
     if (!coord_host || !eigval_host || !msf_host) return SCB_ERR_INVALID;
-    configure_pool_once();
     cudaStream_t st = as_stream(stream);
     const int64_t N = (int64_t)D * n;
     Scratch sc(st);
     double *aos, *soa, *eigval, *msf, *modes = nullptr;
+    int32_t* iters = nullptr;
+    if (iters_host) SCB_TRY(sc.alloc(&iters, (size_t)B));
     SCB_TRY(sc.alloc(&aos, (size_t)B * n * 3));
     SCB_TRY(sc.alloc(&soa, (size_t)B * n * 3));
     SCB_TRY(sc.alloc(&eigval, (size_t)B * k));
@@ -188,13 +213,15 @@ extern "C" int scb_enm_ensemble_host(int D, const double* coord_host, int B, int
     if (modes_host) SCB_TRY(sc.alloc(&modes, (size_t)B * k * N));
     SCB_CUDA(cudaMemcpyAsync(aos, coord_host, sizeof(double) * (size_t)B * n * 3, cudaMemcpyHostToDevice, st));
     SCB_TRY(scb_coords_to_soa(aos, B, n, soa, st));
-    int status = scb_enm_ensemble(D, soa, B, n, ff, patch, masses_dev, k, tol, eigval, msf, modes, nullptr,
+    int status = scb_enm_ensemble(D, soa, B, n, ff, patch, masses_dev, k, tol, eigval, msf, modes, iters,
                                   n_pairs_out, st);
     if (status != SCB_OK && status != SCB_ERR_NOT_CONVERGED) return status;
     SCB_CUDA(cudaMemcpyAsync(eigval_host, eigval, sizeof(double) * (size_t)B * k, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaMemcpyAsync(msf_host, msf, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToHost, st));
     if (modes_host)
         SCB_CUDA(cudaMemcpyAsync(modes_host, modes, sizeof(double) * (size_t)B * k * N, cudaMemcpyDeviceToHost, st));
+    if (iters_host)
+        SCB_CUDA(cudaMemcpyAsync(iters_host, iters, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     return status;
 }

@@ -36,6 +36,7 @@ struct ResLayout {         // device buffers of the resident operator (carved fr
     float* diag32;         // [B][n][12] diagonal blocks (9 used, row-major)
     int32_t* flag;         // [1] != 0: some block is not of the form -v v^T (positive t) -> path unusable
     double* est;           // [B] Lanczos estimate of the largest eigenvalue
+    unsigned long long* app_counter;   // [1] structure x operator applications of the filter launches (profiling)
     int G;                 // groups (= warps) per structure
     int nsplit;            // 16-column layout: the nsplit longest row pairs are split over two slots
     int rec_mul;           // structure s starts at record rec_mul * rowptr[s*n] + rec_pad * s (rounded up to 8)
@@ -57,5 +58,9 @@ int resident_filter(int B, int n, int b, const int64_t* rowptr, const ResLayout&
 // upper spectrum bound from `steps` steps of column-wise Lanczos (FP32, structure-resident): state[s].ub
 int resident_lanczos(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, int steps, uint64_t seed,
                      double ub_factor, EigState* state, cudaStream_t st);
+
+// filter-kernel profile of this process (scb_profile): enabled flag and accumulators
+bool profile_enabled();
+void profile_add(double filter_ms, long long launches, unsigned long long applications);
 
 }  // namespace scb

@@ -161,7 +161,8 @@ resident_filter_kernel(int n, int b, int G, int rec_mul, int64_t rec_pad, const 
                        const uint16_t* __restrict__ order, const float* __restrict__ diag32,
                        const double* X, const double* __restrict__ HX, const double* __restrict__ theta,
                        const double* __restrict__ rn2, const EigState* __restrict__ state,
-                       const int32_t* __restrict__ done, const double* __restrict__ Zr, int nz, double* Xout) {
+                       const int32_t* __restrict__ done, const double* __restrict__ Zr, int nz, double* Xout,
+                       unsigned long long* __restrict__ app_counter) {
     constexpr int LPP = COLS / 4;        // lanes per row pair
     constexpr int RPW = 32 / LPP;        // row pairs per warp (group size)
     extern __shared__ __align__(16) float res_smem[];
@@ -184,6 +185,8 @@ resident_filter_kernel(int n, int b, int G, int rec_mul, int64_t rec_pad, const 
     const EigState e = state[s];
     int deg = e.degree_next;
     deg = deg < 2 ? 2 : (deg > kResDegreeCap ? kResDegreeCap : deg);
+    // bench accounting: operator applications per structure (integer adds commute: the total is reproducible)
+    if (app_counter && tid == 0 && cg == 0) atomicAdd(app_counter, (unsigned long long)(deg - 1));
     const double ehalf = 0.5 * (e.ub - e.lo), cmid = 0.5 * (e.ub + e.lo);
     if (tid < COLS) {
         const int gc = cg * COLS + tid;
@@ -596,12 +599,12 @@ static int launch_filter(int B, int n, int b, const int64_t* rowptr, const ResLa
         SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resident_filter_kernel<COLS, 1><<<grid, 32 * 4 * ((L.G + 3) / 4), smem, st>>>(
             n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz,
-            Xout);
+            Xout, L.app_counter);
     } else {
         SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resident_filter_kernel<COLS, 2><<<grid, 32 * ((L.G + 1) / 2), smem, st>>>(
             n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz,
-            Xout);
+            Xout, L.app_counter);
     }
     SCB_LAUNCH_CHECK();
     return SCB_OK;

@@ -472,7 +472,11 @@ __global__ void state_update_kernel(int B, int b, int k, double tol, const doubl
     EigState e = st[s];
     e.iters += 1;
     double worst = 0.0;
-    const double scale = fmax(fabs(th[k - 1]), 1e-300);
+    // The scale must not collapse when the deflated operator still has zero modes among the wanted ones
+    // (atoms isolated by contact_shutdown, disconnected chains): theta_k ~ 0 there, and a purely relative test
+    // could never pass.  1e-6 * ub is far above the attainable residual (~1e-14 * ub) and far below any
+    // non-trivial eigenvalue of a connected network.
+    const double scale = fmax(fabs(th[k - 1]), 1e-6 * e.ub);
     bool finite = true;   // a NaN Ritz pair must never pass the convergence test (fmax drops NaNs)
     for (int q = 0; q < b; ++q) {
         const double r = sqrt(rn2[(int64_t)s * b + q]);

@@ -275,13 +275,20 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
         _lib.check(h.scb_transpose_small(b, _lib.ptr(modes[0]), _lib.ptr(Cm), st()))
         _lib.check(h.scb_rotate(1, N, b, _lib.ptr(Cm), _lib.ptr(A), _lib.ptr(A), _lib.ptr(HX), _lib.ptr(HX), st()))
         _lib.check(h.scb_residual_norms(1, N, b, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(theta), _lib.ptr(rn2), st()))
+        if op.world > 1:
+            # The replicated tall-skinny steps may differ by rounding between ranks; every decision that steers
+            # the collectives (convergence, filter bounds) is taken on rank 0's values so that all ranks agree.
+            import torch.distributed as dist
+            both = torch.cat([theta, rn2])
+            dist.broadcast(both, src=0)
+            theta, rn2 = both[:b].contiguous(), both[b:].contiguous()
         th = theta.cpu().numpy()
         res = np.sqrt(np.maximum(rn2.cpu().numpy(), 0.0))
         a0 = float(th[0])
         lo = min(float(th[b - 1]), 0.98 * ub)
         if not lo > a0:
             lo = a0 + 0.5 * (ub - a0)
-        if res[:k].max() <= tol * max(abs(th[k - 1]), 1e-300):
+        if res[:k].max() <= tol * max(abs(th[k - 1]), 1e-6 * ub):
             return theta, A, torch.from_numpy(res).cuda(), outer
     raise RuntimeError(_lib.lib().scb_status_string(_lib.SCB_ERR_NOT_CONVERGED).decode())
 

@@ -14,12 +14,22 @@ __all__ = ["enm_ensemble", "enm_ensemble_device", "EnsembleResult"]
 
 
 class EnsembleResult:
-    def __init__(self, eigenvalues, msf, modes, n_pairs, converged):
+    def __init__(self, eigenvalues, msf, modes, n_pairs, converged, iterations=None):
         self.eigenvalues = eigenvalues   # (B, k)   non-trivial modes, ascending
         self.msf = msf                   # (B, n)   MSF from those k modes
         self.modes = modes               # (B, k, N) or None; rows = modes
         self.n_pairs = n_pairs           # ordered contact pairs in the batch
-        self.converged = converged
+        self.converged = converged       # every structure met the tolerance
+        # (B,) outer iterations of the lowest-k solver per structure; NEGATIVE where the structure did not converge
+        # (its rows hold the last iterate); 0 for structures solved by the dense full-spectrum path
+        self.iterations = iterations
+
+    @property
+    def converged_mask(self):
+        """(B,) bool: which structures met the tolerance."""
+        if self.iterations is None:
+            return np.full(len(self.eigenvalues), bool(self.converged))
+        return self.iterations >= 0
 
 
 def _chunk_limit(B):
@@ -60,6 +70,10 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
         return _ensemble_all_modes(coords, force_field, D, masses, return_modes)
     if force_field.natoms is not None and force_field.natoms != n:
         raise ValueError(f"Got coordinates for {n} atoms, but forcefield was built for {force_field.natoms} atoms")
+    if force_field.cutoff_distance is None:
+        # all-pairs force fields (HinsenForceField(), ParameterFreeForceField() defaults) have dense matrices: the
+        # batched full-spectrum solver computes every mode, the k lowest non-trivial ones are kept
+        return _ensemble_all_modes(coords, force_field, D, masses, return_modes, keep=int(k))
     built = force_field._descriptor(n)
     if built is None:
         raise NotImplementedError("user-defined ForceField subclasses are not supported by the batched path")
@@ -75,6 +89,7 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
     # The batch goes through the library in chunks: kernels index structures with blockIdx.y (<= 65,535) and a
     # chunk's scratch must fit the device; on a CUDA out-of-memory status the chunk is halved and retried.
     chunk = _chunk_limit(B)
+    iters = np.zeros(B, dtype=np.int32)
     total_pairs, converged, c0 = 0, True, 0
     while c0 < B:
         c1 = min(B, c0 + chunk)
@@ -83,43 +98,48 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
             D, coords[c0:c1].ctypes.data_as(C.c_void_p), c1 - c0, n, C.byref(desc),
             C.byref(patch) if patch is not None else None, _lib.ptr(m_dev), k, tol,
             eig[c0:c1].ctypes.data_as(C.c_void_p), msf[c0:c1].ctypes.data_as(C.c_void_p),
-            modes[c0:c1].ctypes.data_as(C.c_void_p) if modes is not None else None, C.byref(npairs),
-            _lib.stream_ptr())
+            modes[c0:c1].ctypes.data_as(C.c_void_p) if modes is not None else None,
+            iters[c0:c1].ctypes.data_as(C.c_void_p), C.byref(npairs), _lib.stream_ptr())
         try:
             _lib.check(status, allow=(_lib.SCB_ERR_NOT_CONVERGED,))
         except RuntimeError as err:
             if "out of memory" in str(err).lower() and chunk > 1:
                 chunk = (chunk + 1) // 2
-                torch.cuda.empty_cache()
+                handle.scb_trim_pool()      # the library's cached scratch
+                torch.cuda.empty_cache()    # and the caller's
                 continue
             raise
         total_pairs += int(npairs.value)
         converged = converged and status == 0
         c0 = c1
     del keep
-    return EnsembleResult(eig, msf, modes, total_pairs, converged)
+    return EnsembleResult(eig, msf, modes, total_pairs, converged, iters)
 
 
-def _ensemble_all_modes(coords, force_field, D, masses, return_modes):
-    """All non-trivial modes per conformation: batched assembly -> dense -> block-Jacobi groups -> MSF."""
+def _ensemble_all_modes(coords, force_field, D, masses, return_modes, keep=None):
+    """All non-trivial modes per conformation (or the `keep` lowest of them): batched assembly -> dense ->
+    block-Jacobi groups -> MSF."""
     from . import _engine
     B, n = int(coords.shape[0]), int(coords.shape[1])
     N = D * n
     ntriv = 6 if D == 3 else 1
     if N <= ntriv:
         raise ValueError("system too small: no non-trivial modes")
+    m = N - ntriv if keep is None else keep
+    if m > N - ntriv:
+        raise ValueError(f"{m} non-trivial modes requested, the system has {N - ntriv}")
     chunk = int(max(1, min(64, 2e9 // (40 * N * N))))
-    eig = np.empty((B, N - ntriv))
+    eig = np.empty((B, m))
     msf = np.empty((B, n))
-    modes_out = np.empty((B, N - ntriv, N)) if return_modes else None
+    modes_out = np.empty((B, m, N)) if return_modes else None
     npairs = 0
     for c0 in range(0, B, chunk):
         c1 = min(B, c0 + chunk)
         model = _engine.DeviceModel(coords[c0:c1], force_field, D, masses)
         lam, modes = _engine.eig_full_dense(model.dense())
         npairs += int(model.P)
-        lam_nt = lam[:, ntriv:].contiguous()
-        modes_nt = modes[:, ntriv:, :].contiguous()
+        lam_nt = lam[:, ntriv:ntriv + m].contiguous()
+        modes_nt = modes[:, ntriv:ntriv + m, :].contiguous()
         eig[c0:c1] = lam_nt.cpu().numpy()
         msf[c0:c1] = _engine.modes_msf(D, lam_nt, modes_nt).cpu().numpy()
         if return_modes:

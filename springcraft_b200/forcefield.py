@@ -11,6 +11,7 @@ between the contact kernel and the assembly kernel, doc/advanced.rst:23-70).
 """
 
 import abc
+import functools
 import numbers
 from os.path import dirname, join, realpath
 
@@ -100,21 +101,17 @@ class PatchedForceField(ForceField):
     def __init__(self, force_field, contact_shutdown=None, contact_pair_off=None,
                  contact_pair_on=None, force_constants=None):
         self._force_field = force_field
-        self._contact_shutdown = np.asarray(contact_shutdown) if contact_shutdown is not None else None
-        self._contact_pair_off = np.asarray(contact_pair_off) if contact_pair_off is not None else None
-        self._contact_pair_on = np.asarray(contact_pair_on) if contact_pair_on is not None else None
-        self._force_constants = np.asarray(force_constants) if force_constants is not None else None
-        _check_indices(force_field.natoms, self._contact_shutdown)
-        _check_indices(force_field.natoms, self._contact_pair_off)
-        _check_indices(force_field.natoms, self._contact_pair_on)
-        if self._contact_pair_on is not None:
-            if self._force_constants is None:
-                raise TypeError("Individual force constants must be given, if contacts are turned on")
-            if len(self._force_constants) != len(self._contact_pair_on):
-                raise IndexError(
-                    f"{len(self._force_constants)} force constants were given for "
-                    f"{len(self._contact_pair_on)} switched on contact_pairs"
-                )
+        given = {"_contact_shutdown": contact_shutdown, "_contact_pair_off": contact_pair_off,
+                 "_contact_pair_on": contact_pair_on, "_force_constants": force_constants}
+        for attr, value in given.items():            # any array-like is accepted
+            setattr(self, attr, None if value is None else np.asarray(value))
+        for attr in ("_contact_shutdown", "_contact_pair_off", "_contact_pair_on"):
+            _require_in_range(getattr(self, attr), force_field.natoms)
+        on, fcs = self._contact_pair_on, self._force_constants
+        if on is not None and fcs is None:           # forcefield.py:171-175
+            raise TypeError("Individual force constants must be given, if contacts are turned on")
+        if on is not None and len(fcs) != len(on):   # forcefield.py:176-181
+            raise IndexError(f"{len(fcs)} force constants were given for {len(on)} switched on contact_pairs")
 
     def force_constant(self, atom_i, atom_j, sq_distance):
         if self._force_field._descriptor(1) is None:
@@ -126,23 +123,14 @@ class PatchedForceField(ForceField):
     def cutoff_distance(self):
         return self._force_field.cutoff_distance
 
-    @property
-    def contact_shutdown(self):
-        if self._force_field.contact_shutdown is None:
-            return self._contact_shutdown
-        return np.concatenate([self._contact_shutdown, self._force_field.contact_shutdown])
+    def _stacked(self, name):
+        """Own patch entries followed by those of the wrapped force field (forcefield.py:232-257)."""
+        mine, inner = getattr(self, "_" + name), getattr(self._force_field, name)
+        return mine if inner is None else np.concatenate([mine, inner])
 
-    @property
-    def contact_pair_off(self):
-        if self._force_field.contact_pair_off is None:
-            return self._contact_pair_off
-        return np.concatenate([self._contact_pair_off, self._force_field.contact_pair_off])
-
-    @property
-    def contact_pair_on(self):
-        if self._force_field.contact_pair_on is None:
-            return self._contact_pair_on
-        return np.concatenate([self._contact_pair_on, self._force_field.contact_pair_on])
+    contact_shutdown = property(lambda self: self._stacked("contact_shutdown"))
+    contact_pair_off = property(lambda self: self._stacked("contact_pair_off"))
+    contact_pair_on = property(lambda self: self._stacked("contact_pair_on"))
 
     @property
     def natoms(self):
@@ -287,9 +275,9 @@ class TabulatedForceField(ForceField):
             if not np.all(np.diff(self._edges) >= 0):
                 raise ValueError("Distance bin edges are not sorted in increasing order")
             n_bins = len(self._edges)
-        self._bonded = _convert_to_matrix(bonded, n_bins)
-        self._intra_chain = _convert_to_matrix(intra_chain, n_bins)
-        self._inter_chain = _convert_to_matrix(inter_chain, n_bins)
+        self._bonded = _residue_table(bonded, n_bins)
+        self._intra_chain = _residue_table(intra_chain, n_bins)
+        self._inter_chain = _residue_table(inter_chain, n_bins)
         res_name = np.asarray(atoms.res_name)
         chain_id = np.asarray(atoms.chain_id)
         res_id = np.asarray(atoms.res_id)
@@ -402,51 +390,39 @@ def _e_anm(atoms, intra_file, inter_file, nonbonded_mean):
     return TabulatedForceField(atoms, 82.0, intra, inter, 13.0)
 
 
-def _convert_to_matrix(value, n_bins):
-    """Broadcast to (20, 20, n_bins) float32 (forcefield.py:879-923)."""
+def _residue_table(value, n_bins):
+    """Residue-pair constants as a (20, 20, n_bins) float32 table (what forcefield.py:879-937 accepts):
+    a scalar, one value per distance bin, a symmetric 20x20 matrix or a full symmetric 20x20xk table."""
     if np.isnan(value).any():
         raise IndexError("Array contains NaN elements")
+    full = (N_AMINO_ACIDS, N_AMINO_ACIDS, n_bins)
     if isinstance(value, numbers.Number):
-        return np.full((N_AMINO_ACIDS, N_AMINO_ACIDS, n_bins), value, dtype=np.float32)
-    array = np.asarray(value, dtype=np.float32)
-    if array.ndim == 1:
-        if len(array) != n_bins:
-            raise IndexError(f"Array contains {len(array)} elements for {n_bins} distance bins")
-        return np.ascontiguousarray(np.broadcast_to(array, (N_AMINO_ACIDS, N_AMINO_ACIDS, n_bins)))
-    if array.ndim == 2:
-        _check_matrix(array)
-        return np.repeat(array[..., np.newaxis], n_bins, axis=-1)
-    if array.ndim == 3:
-        _check_matrix(array)
-        if array.shape[-1] != n_bins:
-            raise IndexError(f"Array contains {len(array)} elements for {n_bins} distance bins")
-        return array
-    raise IndexError(f"Expected array with at most 3 dimensions, {array.ndim} given")
+        return np.full(full, value, dtype=np.float32)
+    table = np.asarray(value, dtype=np.float32)
+    if table.ndim not in (1, 2, 3):
+        raise IndexError(f"Expected array with at most 3 dimensions, {table.ndim} given")
+    if table.ndim != 2 and table.shape[-1] != n_bins:
+        raise IndexError(f"Array contains {len(table)} elements for {n_bins} distance bins")
+    if table.ndim >= 2:
+        if table.shape[:2] != full[:2]:
+            raise IndexError(f"Expected matrix of shape {full[:2]}, got {table.shape[:2]}")
+        if not np.allclose(table, table.swapaxes(0, 1)):
+            raise ValueError("Input matrix is not symmetric")
+    if table.ndim == 2:
+        table = table[:, :, None]
+    return np.ascontiguousarray(np.broadcast_to(table, full))
 
 
-def _check_matrix(matrix):
-    """forcefield.py:926-937."""
-    if matrix.shape[:2] != (N_AMINO_ACIDS, N_AMINO_ACIDS):
-        raise IndexError(f"Expected matrix of shape {(N_AMINO_ACIDS, N_AMINO_ACIDS)}, got {matrix.shape[:2]}")
-    axes = (1, 0, 2) if matrix.ndim == 3 else (1, 0)
-    if not np.allclose(matrix, np.transpose(matrix, axes)):
-        raise ValueError("Input matrix is not symmetric")
-
-
-_matrices = {}
-
-
+@functools.lru_cache(maxsize=None)
 def _load_matrix(fname):
-    if fname not in _matrices:
-        _matrices[fname] = np.loadtxt(join(DATA_DIR, fname), delimiter=",")
-    return _matrices[fname]
+    """Comma separated table shipped in data/ (read once per process)."""
+    return np.loadtxt(join(DATA_DIR, fname), delimiter=",")
 
 
-def _check_indices(length, indices):
-    """forcefield.py:953-962."""
+def _require_in_range(indices, length):
+    """Patch indices must address atoms of the structure the force field was built for (forcefield.py:953-962)."""
     if indices is None or length is None:
         return
-    flat = indices.flatten()
-    oob = np.where(flat >= length)[0]
-    if len(oob) > 0:
-        raise IndexError(f"Index {flat[oob[0]]} is out of bounds for a structure of length {length}")
+    beyond = indices[indices >= length]
+    if beyond.size:
+        raise IndexError(f"Index {beyond.flat[0]} is out of bounds for a structure of length {length}")

@@ -165,8 +165,10 @@ def normal_mode(anm, index, amplitude, frames, movement="sine"):
     return out.cpu().numpy()
 
 
-def linear_response(anm, force):
-    """nma.py:422-473."""
+def linear_response(anm, force, *, mode_subset=None):
+    """nma.py:422-473.  ``mode_subset`` (keyword-only extension, SURVEY 8a18 / BASELINE config C5: "linear response
+    from m modes") restricts the pseudo-inverse to the given non-trivial modes: V_S^T (L_S^-1 (V_S f)); small
+    subsets are served by the lowest-k solver, so no full decomposition is needed."""
     from .anm import ANM
     if not isinstance(anm, ANM):
         raise ValueError("Instance of ANM class expected.")
@@ -183,7 +185,10 @@ def linear_response(anm, force):
         raise ValueError(f"Expected 1D or 2D array, got {force.ndim} dimensions")
     import torch
     from . import _lib
-    lam, modes = _pinv_modes(anm)
+    if mode_subset is None:
+        lam, modes = _pinv_modes(anm)
+    else:
+        lam, modes = _select(anm, mode_subset, 6)
     f = _lib.to_device(force.astype(np.float64), torch.float64)
     return _engine.modes_linear_response(lam, modes, f).cpu().numpy().reshape(n, 3)
 

@@ -317,13 +317,24 @@ def ref_synthetic():
     sq = np.square(vec.T[sub]).reshape(100, n, 3).sum(-1)
     save("ref_c4_cloud400.npz", coord=coord, eigval=lam[:130], modes_6_106=vec.T[6:106],
          msf_6_106=(sq / lam[sub][:, None]).sum(0), hessian_diag=np.diagonal(H).copy())
-    # C5 (scaled down): DCC + linear response from a mode subset
+    ref_c5()
+
+
+def ref_c5():
+    """C5 (scaled down): DCC + linear response, full covariance and a mode subset ("from m modes")."""
     n = 400
     coord = orc.synthetic_chain(n, seed=3)
     anm = springcraft.ANM(coord, springcraft.InvariantForceField(13.0))
     gnm = springcraft.GNM(coord, springcraft.InvariantForceField(10.0))
     rng = np.random.default_rng(11)
     f = rng.normal(size=(n, 3))
+    # the reference has no truncated linear response (nma.py:473 multiplies with the full pseudo-inverse); the
+    # low-rank form V_S^T (L_S^-1 (V_S f)) is evaluated here from the reference's own eigen() output
+    lam, vec = anm.eigen()
+    sub = np.arange(6, 56)
+    lr_sub = (vec[sub].T @ ((vec[sub] @ f.flatten()) / lam[sub])).reshape(n, 3)
+    unit = np.zeros((n, 3))
+    unit[42, 0] = 1.0                       # doc/index.rst:139-142
     save("ref_c5_chain400.npz", coord=coord, force=f,
          anm_dcc_sub=anm.dcc(mode_subset=np.arange(6, 56)),
          anm_dcc_sub_abs=anm.dcc(mode_subset=np.arange(6, 56), norm=False),
@@ -331,8 +342,32 @@ def ref_synthetic():
          gnm_dcc_sub=gnm.dcc(mode_subset=np.arange(1, 51)),
          gnm_dcc_all_abs=gnm.dcc(norm=False),
          anm_lr=anm.linear_response(f),
+         anm_lr_unit42=anm.linear_response(unit),
+         anm_lr_sub=lr_sub,
          anm_msf=anm.mean_square_fluctuation(),
          gnm_msf=gnm.mean_square_fluctuation())
+
+
+def ref_dense_table():
+    """TabulatedForceField whose interaction_matrix was edited in place by the user (forcefield.py:429-434):
+    the edited (n,n,k) float32 table is what force_constant() reads."""
+    ca = load_ca("1l2y.pdb")
+    out = {}
+    for key in ("e_anm", "sd_enm"):
+        ff = FF_BUILDERS[key](ca)
+        M = ff.interaction_matrix
+        rng = np.random.default_rng(5)
+        for _ in range(12):
+            i, j = rng.integers(0, len(ca), size=2)
+            if i == j:
+                continue
+            fac = np.float32(rng.uniform(0.25, 3.0))
+            M[i, j] *= fac
+            M[j, i] = M[i, j]
+        out[f"{key}/table"] = M.copy()
+        out[f"{key}/hessian"], out[f"{key}/pairs"] = springcraft.compute_hessian(ca.coord, ff)
+        out[f"{key}/kirchhoff"], _ = springcraft.compute_kirchhoff(ca.coord, ff)
+    save("ref_dense_table.npz", **out)
 
 
 FUZZ_KINDS = ["invariant", "hinsen", "hinsen_nocut", "pfree", "pfree_nocut", "e_anm", "e_anm_mean", "e_anm_mj",
@@ -410,6 +445,6 @@ def ref_fuzz():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["structures", "ref_1l2y", "ref_two_chain", "thirdparty",
-                             "ref_random500", "ref_7cal", "ref_synthetic", "ref_fuzz"]
+                             "ref_random500", "ref_7cal", "ref_synthetic", "ref_fuzz", "ref_dense_table"]
     for w in which:
         globals()[w]()

@@ -714,3 +714,43 @@ def test_c5_dcc_linear_response():
     assert np.allclose(anm.dcc(mode_subset=np.arange(6, 56), norm=False), ref["anm_dcc_sub_abs"],
                        rtol=1e-8, atol=1e-10 * np.abs(ref["anm_dcc_sub_abs"]).max())
     assert np.allclose(gnm.dcc(mode_subset=np.arange(1, 51)), ref["gnm_dcc_sub"], atol=1e-8)
+    # full covariance products (nma.py:324-336, 473) and the default mode set of the MSF (nma.py:145-151)
+    assert np.allclose(anm.dcc(), ref["anm_dcc_all"], atol=1e-8)
+    assert np.allclose(gnm.dcc(norm=False), ref["gnm_dcc_all_abs"], rtol=1e-8,
+                       atol=1e-10 * np.abs(ref["gnm_dcc_all_abs"]).max())
+    assert np.allclose(anm.mean_square_fluctuation(), ref["anm_msf"], rtol=PROD_RTOL)
+    assert np.allclose(gnm.mean_square_fluctuation(), ref["gnm_msf"], rtol=PROD_RTOL)
+    scale = np.abs(ref["anm_lr"]).max()
+    assert np.allclose(anm.linear_response(ref["force"]), ref["anm_lr"], rtol=1e-8, atol=1e-10 * scale)
+    assert np.allclose(anm.linear_response(ref["force"].flatten()), ref["anm_lr"], rtol=1e-8, atol=1e-10 * scale)
+    unit = np.zeros((len(coord), 3))
+    unit[42, 0] = 1.0
+    assert np.allclose(anm.linear_response(unit), ref["anm_lr_unit42"], rtol=1e-8,
+                       atol=1e-10 * np.abs(ref["anm_lr_unit42"]).max())
+    # "from m modes": low-rank response V_S^T L_S^-1 V_S f through the lowest-k solver (fresh object: no cached spectrum)
+    low = sc.ANM(coord, sc.InvariantForceField(13.0))
+    got = low.linear_response(ref["force"], mode_subset=np.arange(6, 56))
+    assert low._spectrum_cache.get("full") is None, "the subset must not trigger a full decomposition"
+    assert np.allclose(got, ref["anm_lr_sub"], rtol=1e-7, atol=1e-9 * np.abs(ref["anm_lr_sub"]).max())
+    with pytest.raises(ValueError):
+        low.linear_response(ref["force"], mode_subset=np.arange(5, 20))
+
+
+def test_tabulated_interaction_matrix_edited_in_place(structures):
+    """forcefield.py:429-434: interaction_matrix is returned by reference; edits by the caller are what
+    force_constant() uses (device side: SCB_FF_TABULATED_DENSE reads the explicit (n,n,k) float32 table)."""
+    ref = golden("ref_dense_table.npz")
+    atoms = atoms_of(structures, "1l2y")
+    for key in ("e_anm", "sd_enm"):
+        ff = FF[key](atoms)
+        M = ff.interaction_matrix
+        assert M.dtype == np.float32 and ff.interaction_matrix is M
+        M[...] = ref[f"{key}/table"]
+        H, pairs = sc.compute_hessian(atoms.coord, ff)
+        assert np.array_equal(pairs, ref[f"{key}/pairs"])
+        assert np.array_equal(H, ref[f"{key}/hessian"])
+        K, _ = sc.compute_kirchhoff(atoms.coord, ff)
+        assert np.array_equal(K, ref[f"{key}/kirchhoff"])
+        # the pristine force field gives a different matrix: the edit really went through the dense table
+        H0, _ = sc.compute_hessian(atoms.coord, FF[key](atoms))
+        assert not np.array_equal(H0, H)

@@ -58,6 +58,9 @@ for ex in ("peer", "nccl"):
     outs.append(op.apply(Xb).clone()); outs.append(op.apply(Xb, Xb, (0.5, 0.1, 0.25)).clone())
     op.close()
 assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3]), "fused all-gather differs from NCCL all-gather"
+# the oracle-free checks that bench.py --gpus N also runs (C4 peer/nccl, borderline tolerance, C5 slabs, C3 shards)
+from tests.multigpu_checks import run_checks
+run_checks()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -72,6 +75,6 @@ def test_two_gpu_partitioned_paths(tmp_path):
     env = dict(os.environ, SCB_ROOT=ROOT)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
-                         env=env, capture_output=True, text=True, timeout=600)
+                         env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2

@@ -269,3 +269,39 @@ def test_fuzz_cases_bit_exact(i):
     lam, modes = orc.eigen(Km)
     assert np.array_equal(lam, ref[pre + "gnm_eigval"])
     assert np.allclose(orc.mean_square_fluctuation(lam, modes, 1), ref[pre + "gnm_msf"], rtol=1e-11)
+
+
+def test_c5_chain400_products():
+    """C5 scaled down (reference outputs, make_golden.py::ref_c5): DCC, MSF and the linear response from the full
+    pseudo-inverse and from a mode subset."""
+    ref = golden("ref_c5_chain400.npz")
+    coord = ref["coord"]
+    H, _ = orc.compute_hessian(coord, orc.FFSpec("invariant", 13.0))
+    lam, modes = orc.eigen(H)
+    cov = orc.covariance(H)
+    scale = np.abs(ref["anm_lr"]).max()
+    assert np.allclose(orc.linear_response(cov, ref["force"]), ref["anm_lr"], rtol=1e-9, atol=1e-11 * scale)
+    unit = np.zeros((len(coord), 3))
+    unit[42, 0] = 1.0
+    assert np.allclose(orc.linear_response(cov, unit), ref["anm_lr_unit42"], rtol=1e-9,
+                       atol=1e-11 * np.abs(ref["anm_lr_unit42"]).max())
+    got = orc.linear_response_modes(lam, modes, ref["force"], np.arange(6, 56))
+    assert np.allclose(got, ref["anm_lr_sub"], rtol=1e-9, atol=1e-11 * np.abs(ref["anm_lr_sub"]).max())
+    assert np.allclose(orc.mean_square_fluctuation(lam, modes, 3), ref["anm_msf"], rtol=1e-10)
+    assert np.allclose(orc.dcc(lam, modes, 3, mode_subset=np.arange(6, 56)), ref["anm_dcc_sub"], atol=1e-10)
+    assert np.allclose(orc.dcc(lam, modes, 3, cov=cov), ref["anm_dcc_all"], atol=1e-10)
+
+
+def test_dense_table_edited_in_place(structures):
+    """forcefield.py:429-434: an interaction_matrix edited by the caller is the table force_constant() reads."""
+    ref = golden("ref_dense_table.npz")
+    coord = structures["1l2y_coord"].astype(np.float64)
+    s = seq(structures, "1l2y")
+    for key in ("e_anm", "sd_enm"):
+        spec = orc.preset_spec(key, *s)
+        spec.extra["dense_table"] = ref[f"{key}/table"]
+        H, pairs = orc.compute_hessian(coord, spec)
+        K, _ = orc.compute_kirchhoff(coord, spec)
+        assert np.array_equal(pairs, ref[f"{key}/pairs"])
+        assert np.array_equal(H, ref[f"{key}/hessian"])
+        assert np.array_equal(K, ref[f"{key}/kirchhoff"])
