@@ -13,6 +13,9 @@ constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs (grid sizing only)
 
 void set_last_cuda_error(cudaError_t e, const char* file, int line);
 void count_launches(int n);  // process-wide kernel launch counter (scb_launch_count)
+// stream-ordered scratch from the library-private memory pool of the current device (pipeline.cu)
+int pool_alloc(void** p, size_t bytes, cudaStream_t st);
+void pool_free(void* p, cudaStream_t st);
 
 #define SCB_CUDA(expr)                                              \
     do {                                                            \

@@ -388,11 +388,8 @@ extern "C" int scb_gram(int B, int64_t N, int b, const double* A, const double* 
 extern "C" int scb_chol_orth(int B, int b, const double* S, double* C, void* stream) {
     if (!S || !C || B < 1 || b < 1 || b > 160) return SCB_ERR_INVALID;
     const size_t smem = sizeof(double) * (size_t)b * (b + 1);
-    static bool configured = false;
-    if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(chol_orth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 161 * 8));
-        configured = true;
-    }
+    // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+    SCB_CUDA(cudaFuncSetAttribute(chol_orth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 161 * 8));
     chol_orth_kernel<<<B, 256, smem, as_stream(stream)>>>(b, S, C);
     SCB_LAUNCH_CHECK();
     return SCB_OK;

@@ -375,12 +375,9 @@ int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void*
     const int npairs = nb / 2;
     const size_t smem_pivot = sizeof(double) * 2 * kPW * (kPW + 1);
     const size_t smem_tile = sizeof(double) * 3 * kPW * kTLD;
-    static bool configured = false;
-    if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(bj_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pivot));
-        SCB_CUDA(cudaFuncSetAttribute(bj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
-        configured = true;
-    }
+    // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+    SCB_CUDA(cudaFuncSetAttribute(bj_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pivot));
+    SCB_CUDA(cudaFuncSetAttribute(bj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
     int inner_sweeps = 1;
     if (const char* env = getenv("SCB_BJ_INNER")) inner_sweeps = atoi(env) > 0 ? atoi(env) : inner_sweeps;
     int cross = 1;

@@ -66,6 +66,14 @@ static cudaMemPool_t device_pool() {
     return g_pools[dev];
 }
 
+int pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+    cudaMemPool_t pool = device_pool();
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(p, bytes, pool, st) : cudaMallocAsync(p, bytes, st);
+    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return SCB_ERR_CUDA; }
+    return SCB_OK;
+}
+void pool_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
 struct Scratch {
     cudaStream_t st;
     cudaMemPool_t pool;

@@ -338,11 +338,8 @@ static int run_product(int D, int n, int m, const double* lam, const double* mod
     const int Mrows = row1 - row0;
     dim3 grid((unsigned)ceil_div(n, kGemmBN), (unsigned)ceil_div(Mrows, kGemmBM));
     const size_t smem = sizeof(double) * 2 * (kGemmBM + kGemmBN) * kGemmLD;
-    static bool configured = false;
-    if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+    SCB_CUDA(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_nt_dmma_kernel<<<grid, 256, smem, st>>>(Mrows, n, K, ldk, row0, Aop, Bop, norm ? dn : nullptr, scale, out, n);
     SCB_LAUNCH_CHECK();
     return SCB_OK;

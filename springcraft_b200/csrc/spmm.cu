@@ -233,11 +233,8 @@ template <int D, int C>
 static int spmm_struct_launch(int B, int n, const int64_t* rowptr, const int32_t* col, const double* offdiag,
                               const double* diag, const double* X, const double* W, double* Y, const double* coef,
                               int coef_stride, const int32_t* done, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {  // give L1 as much of the unified array as possible
-        cudaFuncSetAttribute(spmm_struct_kernel<D, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-        configured = true;
-    }
+    // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag --   give L1 as much of the unified array as possible
+    cudaFuncSetAttribute(spmm_struct_kernel<D, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     // whole structures per CTA up to 512 rows; larger ones in chunks of 256 rows
     const int rows_per_cta = n <= 512 ? n : 256;
     dim3 grid((unsigned)ceil_div(n, rows_per_cta), (unsigned)B);

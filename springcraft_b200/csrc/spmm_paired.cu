@@ -269,11 +269,8 @@ static int launch_paired(dim3 grid, int n, int np, int per_cta, const int64_t* r
                          const void* pent, const double* X, const double* W, double* Y, const double* coef,
                          int coef_stride, const int32_t* done, cudaStream_t st) {
     const size_t smem = sizeof(PairEntry<D>) * 2 * kPairChunk * kPairWarps + sizeof(uint64_t) * 2 * kPairWarps;
-    static bool configured = false;
-    if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<D, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+    SCB_CUDA(cudaFuncSetAttribute(spmm_paired_kernel<D, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     spmm_paired_kernel<D, BC><<<grid, kPairWarps * 32, smem, st>>>(n, np, per_cta, rowptr, pcount,
                                                              static_cast<const PairEntry<D>*>(pent), X, W, Y, coef,
                                                              coef_stride, done);

@@ -234,11 +234,8 @@ static int launch_paired32(dim3 grid, int n, int np, int per_cta, const int64_t*
                            const int32_t* pcount, const void* pent, const float* X, const float* W, float* Y,
                            const double* coef, int coef_stride, const int32_t* skip, cudaStream_t st) {
     const size_t smem = sizeof(PairEntry32<D>) * 2 * kPairChunk * kPair32Warps + sizeof(uint64_t) * 2 * kPair32Warps;
-    static bool configured = false;
-    if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(spmm_paired_f32_kernel<D, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+    SCB_CUDA(cudaFuncSetAttribute(spmm_paired_f32_kernel<D, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     spmm_paired_f32_kernel<D, BC><<<grid, kPair32Warps * 32, smem, st>>>(
         n, np, per_cta, rowptr, pcount, static_cast<const PairEntry32<D>*>(pent), X, W, Y, coef, coef_stride, skip);
     SCB_LAUNCH_CHECK();

@@ -11,7 +11,34 @@
 namespace scb {
 
 // ---------------------------------------------------------------------------
-// G[s] += A[s]^T B[s]   (A, B: [N][BW] row-major; G: [BW][BW]);  G pre-zeroed
+// Reductions over the rows of a tall block are split over several CTAs per structure.  Every CTA writes its partial
+// result to its own slot and a second kernel adds the slots in index order: fixed summation order, no atomicAdd on
+// doubles, results reproducible run to run.
+// out[s][q] = sum_c part[s][c][q]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sum_chunks_kernel(int64_t per_struct, int chunks, const double* __restrict__ part, double* __restrict__ out,
+                  const int32_t* __restrict__ done) {
+    const int64_t s = blockIdx.y;
+    if (done && done[s]) return;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= per_struct) return;
+    const double* p = part + s * chunks * per_struct + q;
+    double t = 0.0;
+    for (int c = 0; c < chunks; ++c) t += p[(int64_t)c * per_struct];
+    out[s * per_struct + q] = t;
+}
+
+static int sum_chunks(int B, int64_t per_struct, int chunks, const double* part, double* out, const int32_t* done,
+                      cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(per_struct, 256), (unsigned)B);
+    sum_chunks_kernel<<<grid, 256, 0, st>>>(per_struct, chunks, part, out, done);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// G[s] = A[s]^T B[s]   (A, B: [N][BW] row-major; G: [BW][BW]); partial Gram matrix of the CTA's rows -> its slot
 // ---------------------------------------------------------------------------
 constexpr int kGramRows = 512;  // rows of the tall matrices reduced by one CTA
 
@@ -57,22 +84,29 @@ gram_kernel(int64_t N, const double* __restrict__ A, const double* __restrict__ 
                 for (int j = 0; j < TT; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
     }
-    double* Gs = G + (int64_t)s * BW * BW;
+    double* Gs = G + ((int64_t)s * gridDim.x + blockIdx.x) * BW * BW;
 #pragma unroll
     for (int i = 0; i < TT; ++i)
 #pragma unroll
-        for (int j = 0; j < TT; ++j) atomicAdd(&Gs[(ty * TT + i) * BW + tx * TT + j], acc[i][j]);
+        for (int j = 0; j < TT; ++j) Gs[(ty * TT + i) * BW + tx * TT + j] = acc[i][j];
 }
 
 int gram(int B, int64_t N, int b, const double* A, const double* Bm, double* G, const int32_t* done,
          cudaStream_t st) {
-    SCB_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)B * b * b, st));
-    dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
-    if (b == 32) gram_kernel<32><<<grid, 256, 0, st>>>(N, A, Bm, G, done);
-    else if (b == 64) gram_kernel<64><<<grid, 256, 0, st>>>(N, A, Bm, G, done);
-    else if (b == 128) gram_kernel<128><<<grid, 256, 0, st>>>(N, A, Bm, G, done);
-    else return SCB_ERR_UNSUPPORTED;
+    if (b != 32 && b != 64 && b != 128) return SCB_ERR_UNSUPPORTED;
+    const int chunks = (int)ceil_div(N, kGramRows);
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    double* part = G;          // a single chunk writes the result directly
+    if (chunks > 1) SCB_TRY(pool_alloc((void**)&part, sizeof(double) * (size_t)B * chunks * b * b, st));
+    if (b == 32) gram_kernel<32><<<grid, 256, 0, st>>>(N, A, Bm, part, done);
+    else if (b == 64) gram_kernel<64><<<grid, 256, 0, st>>>(N, A, Bm, part, done);
+    else gram_kernel<128><<<grid, 256, 0, st>>>(N, A, Bm, part, done);
     SCB_LAUNCH_CHECK();
+    if (chunks > 1) {
+        const int status = sum_chunks(B, (int64_t)b * b, chunks, part, G, done, st);
+        pool_free(part, st);
+        return status;
+    }
     return SCB_OK;
 }
 
@@ -203,11 +237,8 @@ int small_rr(int B, int b, const double* S, const double* T, double* theta, doub
         rr_kernel<32><<<B, 256, smem, st>>>(S, T, theta, C, done, mode, nact);
     } else if (b == 64) {
         const size_t smem = sizeof(double) * 3 * 64 * 65;
-        static bool configured = false;
-        if (!configured) {
-            SCB_CUDA(cudaFuncSetAttribute(rr_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+        SCB_CUDA(cudaFuncSetAttribute(rr_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rr_kernel<64><<<B, 256, smem, st>>>(S, T, theta, C, done, mode, nact);
     } else {
         return SCB_ERR_UNSUPPORTED;
@@ -271,11 +302,8 @@ int rotate(int B, int64_t N, int b, const double* C, const double* Xin, double* 
     } else if (b == 64) {
         rotate_kernel<64><<<grid, 256, smem, st>>>(N, C, Xin, Xout, Yin, Yout, done);
     } else if (b == 128) {
-        static bool configured = false;
-        if (!configured) {
-            SCB_CUDA(cudaFuncSetAttribute(rotate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        // per-device function attribute: set on every launch (cheap), no process-wide "configured" flag
+        SCB_CUDA(cudaFuncSetAttribute(rotate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rotate_kernel<128><<<grid, 256, smem, st>>>(N, C, Xin, Xout, Yin, Yout, done);
     } else {
         return SCB_ERR_UNSUPPORTED;
@@ -319,12 +347,22 @@ ztx_kernel(int64_t N, int nz, const double* __restrict__ Z, const double* __rest
                 for (int cc = 0; cc < CC; ++cc) acc[z][cc] = fma(zv, x[cc], acc[z][cc]);
             }
     }
-    // one atomic per warp, null vector and column (nz * BW * 8 per CTA)
+    // warps of the CTA in index order -> the CTA's slot P[s][chunk][z][column]
+    __shared__ double red[kMaxNz][BW];
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int z = 0; z < kMaxNz; ++z)
-        if (z < nz)
+            for (int z = 0; z < kMaxNz; ++z)
 #pragma unroll
-            for (int cc = 0; cc < CC; ++cc) atomicAdd(&P[((int64_t)s * kMaxNz + z) * BW + lane + 32 * cc], acc[z][cc]);
+                for (int cc = 0; cc < CC; ++cc) {
+                    double* r = &red[z][lane + 32 * cc];
+                    *r = (w == 0 ? 0.0 : *r) + acc[z][cc];
+                }
+        }
+        __syncthreads();
+    }
+    double* Ps = P + ((int64_t)s * gridDim.x + blockIdx.x) * kMaxNz * BW;
+    for (int q = threadIdx.x; q < kMaxNz * BW; q += 256) Ps[q] = red[q / BW][q % BW];
 }
 
 template <int CC>
@@ -361,23 +399,23 @@ int deflate(int B, int64_t N, int b, int nz, const double* Z, double* X, double*
             cudaStream_t st) {
     if (nz <= 0 || !Z) return SCB_OK;
     if (nz > kMaxNz) return SCB_ERR_UNSUPPORTED;
-    SCB_CUDA(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)B * kMaxNz * b, st));
-    dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
-    if (b == 32) {
-        ztx_kernel<1><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
-        subz_kernel<1><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
-        count_launches(1);
-    } else if (b == 64) {
-        ztx_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
-        subz_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
-        count_launches(1);
-    } else if (b == 128) {
-        ztx_kernel<4><<<grid, 256, 0, st>>>(N, nz, Z, X, P, done);
-        subz_kernel<4><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
-        count_launches(1);
-    } else {
-        return SCB_ERR_UNSUPPORTED;
+    if (b != 32 && b != 64 && b != 128) return SCB_ERR_UNSUPPORTED;
+    const int chunks = (int)ceil_div(N, kGramRows);
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    double* part = P;
+    if (chunks > 1) SCB_TRY(pool_alloc((void**)&part, sizeof(double) * (size_t)B * chunks * kMaxNz * b, st));
+    if (b == 32) ztx_kernel<1><<<grid, 256, 0, st>>>(N, nz, Z, X, part, done);
+    else if (b == 64) ztx_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, X, part, done);
+    else ztx_kernel<4><<<grid, 256, 0, st>>>(N, nz, Z, X, part, done);
+    SCB_LAUNCH_CHECK();
+    if (chunks > 1) {
+        const int status = sum_chunks(B, (int64_t)kMaxNz * b, chunks, part, P, done, st);
+        pool_free(part, st);
+        if (status != SCB_OK) return status;
     }
+    if (b == 32) subz_kernel<1><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
+    else if (b == 64) subz_kernel<2><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
+    else subz_kernel<4><<<grid, 256, 0, st>>>(N, nz, Z, P, X, done);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
@@ -414,19 +452,27 @@ resid_kernel(int64_t N, const double* __restrict__ X, const double* __restrict__
     for (int c = threadIdx.x; c < BW; c += 256) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += red[w][c];
-        atomicAdd(&rn2[(int64_t)s * BW + c], t);
+        rn2[((int64_t)s * gridDim.x + blockIdx.x) * BW + c] = t;
     }
 }
 
 int residual_norms(int B, int64_t N, int b, const double* X, const double* HX, const double* theta, double* rn2,
                    const int32_t* done, cudaStream_t st) {
-    // rn2 of converged structures must survive: zero only the active ones
-    dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
-    if (b == 32) resid_kernel<1><<<grid, 256, 0, st>>>(N, X, HX, theta, rn2, done);
-    else if (b == 64) resid_kernel<2><<<grid, 256, 0, st>>>(N, X, HX, theta, rn2, done);
-    else if (b == 128) resid_kernel<4><<<grid, 256, 0, st>>>(N, X, HX, theta, rn2, done);
-    else return SCB_ERR_UNSUPPORTED;
+    // rn2 of converged structures survives: their CTAs and their final sums are skipped
+    if (b != 32 && b != 64 && b != 128) return SCB_ERR_UNSUPPORTED;
+    const int chunks = (int)ceil_div(N, kGramRows);
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    double* part = rn2;
+    if (chunks > 1) SCB_TRY(pool_alloc((void**)&part, sizeof(double) * (size_t)B * chunks * b, st));
+    if (b == 32) resid_kernel<1><<<grid, 256, 0, st>>>(N, X, HX, theta, part, done);
+    else if (b == 64) resid_kernel<2><<<grid, 256, 0, st>>>(N, X, HX, theta, part, done);
+    else resid_kernel<4><<<grid, 256, 0, st>>>(N, X, HX, theta, part, done);
     SCB_LAUNCH_CHECK();
+    if (chunks > 1) {
+        const int status = sum_chunks(B, b, chunks, part, rn2, done, st);
+        pool_free(part, st);
+        return status;
+    }
     return SCB_OK;
 }
 
@@ -645,7 +691,7 @@ coldot_kernel(int64_t N, const double* __restrict__ A, const double* __restrict_
     for (int c = threadIdx.x; c < BW; c += 256) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += red[w][c];
-        atomicAdd(&out[(int64_t)s * BW + c], t);
+        out[((int64_t)s * gridDim.x + blockIdx.x) * BW + c] = t;
     }
 }
 
@@ -734,12 +780,19 @@ __global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restri
 }
 
 int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st) {
-    SCB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)B * b, st));
-    dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
-    if (b == 32) coldot_kernel<1><<<grid, 256, 0, st>>>(N, A, Bm, out);
-    else if (b == 64) coldot_kernel<2><<<grid, 256, 0, st>>>(N, A, Bm, out);
-    else return SCB_ERR_UNSUPPORTED;
+    if (b != 32 && b != 64) return SCB_ERR_UNSUPPORTED;
+    const int chunks = (int)ceil_div(N, kGramRows);
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    double* part = out;
+    if (chunks > 1) SCB_TRY(pool_alloc((void**)&part, sizeof(double) * (size_t)B * chunks * b, st));
+    if (b == 32) coldot_kernel<1><<<grid, 256, 0, st>>>(N, A, Bm, part);
+    else coldot_kernel<2><<<grid, 256, 0, st>>>(N, A, Bm, part);
     SCB_LAUNCH_CHECK();
+    if (chunks > 1) {
+        const int status = sum_chunks(B, b, chunks, part, out, nullptr, st);
+        pool_free(part, st);
+        return status;
+    }
     return SCB_OK;
 }
 

@@ -86,6 +86,17 @@ def residue_mass(res_name):
         return _RES_MASS[res_name]
 
 
+def _is_alpha_carbon(line):
+    """ATOM/HETATM line of a C-alpha: atom name CA and element C.  When the element columns are blank the column
+    alignment of the name decides: one-letter elements start in column 14 (" CA "), calcium is written "CA  "."""
+    if line[12:16].strip() != "CA":
+        return False
+    element = line[76:78].strip().upper()
+    if element:
+        return element == "C"
+    return line[12] == " "
+
+
 def read_pdb_ca(path, model=1):
     """CA trace of the given model of a PDB file (first altloc only)."""
     rows = []
@@ -101,7 +112,7 @@ def read_pdb_ca(path, model=1):
             elif rec in ("ATOM  ", "HETATM") and current == model:
                 if line[16] not in (" ", "A"):
                     continue
-                if line[12:16].strip() == "CA" and line[76:78].strip().upper() in ("C", ""):
+                if _is_alpha_carbon(line):
                     rows.append(line)
     return AtomArray(
         np.array([[float(l[30:38]), float(l[38:46]), float(l[46:54])] for l in rows], dtype=np.float32),
@@ -123,7 +134,7 @@ def _pdb_ca_rows(fh):
             if cur is None:          # file without MODEL records
                 cur = []
                 models.append(cur)
-            if line[16] in (" ", "A") and line[12:16].strip() == "CA" and line[76:78].strip().upper() in ("C", ""):
+            if line[16] in (" ", "A") and _is_alpha_carbon(line):
                 cur.append(line)
         elif rec.startswith("ENDMDL"):
             cur = None
@@ -149,8 +160,10 @@ def read_pdb_ca_models(path):
         chain_id=np.array([l[21].strip() for l in first]),
         res_id=np.array([int(l[22:26]) for l in first]),
     )
+    # rounded through float32 like AtomArray.coord (biotite stores float32; the reference widens that to float64,
+    # interaction.py:43,88), so that model k of the bundle and read_pdb_ca(path, model=k) give identical matrices
     coords = np.array([[[float(l[30:38]), float(l[38:46]), float(l[46:54])] for l in rows] for rows in models],
-                      dtype=np.float64)
+                      dtype=np.float32).astype(np.float64)
     return atoms, coords
 
 

@@ -239,6 +239,10 @@ def test_read_pdb_ca(tmp_path):
     assert np.allclose(ca.coord[1], [-4.923, 4.002, -2.452])
     ff = sc.TabulatedForceField.e_anm(ca)
     assert ff.natoms == 3 and ff._bonded_next.tolist() == [1, 0, 0]
+    # blank element columns: the alignment of the atom name tells C-alpha (" CA ") from calcium ("CA  ")
+    blank = tmp_path / "blank.pdb"
+    blank.write_text("\n".join(l[:76].rstrip() if l.startswith(("ATOM", "HETATM")) else l for l in lines) + "\n")
+    assert len(sc.read_pdb_ca(str(blank))) == 3
 
 
 def test_read_pdb_ca_models(tmp_path):
@@ -254,7 +258,9 @@ def test_read_pdb_ca_models(tmp_path):
     path.write_text("\n".join(model(1, 0.0) + model(2, 0.5) + model(3, 1.0)) + "\n")
     atoms, coords = sc.read_pdb_ca_models(str(path))
     assert len(atoms) == 3 and coords.shape == (3, 3, 3) and coords.dtype == np.float64
-    assert np.allclose(coords[:, 0, 0], [-8.608, -8.108, -7.608]) and np.allclose(coords[0], atoms.coord)
+    assert np.allclose(coords[:, 0, 0], [-8.608, -8.108, -7.608]) and np.array_equal(coords[0], atoms.coord)
+    # every model is rounded through float32 exactly like the single-model reader
+    assert np.array_equal(coords[1], sc.read_pdb_ca(str(path), model=2).coord.astype(np.float64))
     assert atoms.chain_id.tolist() == ["A", "A", "B"]
     bad = tmp_path / "bad.pdb"
     extra = "ATOM      5  CA  GLY B   4       0.000   0.000   0.000  1.00  0.00           C  "
