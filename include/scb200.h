@@ -237,6 +237,18 @@ int scb_residual_norms(int B, int64_t N, int b, const double *X, const double *H
                        const double *theta, double *rn2, void *stream);
 /* out = in^T for a b x b matrix (mode rows -> rotation columns) */
 int scb_transpose_small(int b, const double *in, double *out, void *stream);
+/* Column-wise Lanczos (every column of a block is an independent Lanczos run; spectrum bound of an operator the
+ * caller applies, e.g. the dense row-slab operator).  b = 32, 64 or 128.
+ *   scb_coldot:        out[B][b] = column-wise dot products of A and Bm ([B][N][b])
+ *   scb_lanczos_axpy:  mode 0: W <- W - alpha V - sqrt(beta_prev) Vprev   (beta_prev may be NULL)
+ *                      mode 1: Vprev <- V, V <- W / sqrt(nrm2)       mode 2: V <- V / sqrt(nrm2)
+ *   scb_lanczos_bound: out[B] = factor * max over the columns of the largest eigenvalue of the steps x steps
+ *                      tridiagonal (alpha[steps][B][b], beta2[steps][B][b] = squared couplings) */
+int scb_coldot(int B, int64_t N, int b, const double *A, const double *Bm, double *out, void *stream);
+int scb_lanczos_axpy(int B, int64_t N, int b, int mode, double *V, double *Vprev, double *W,
+                     const double *alpha, const double *beta_prev, const double *nrm2, void *stream);
+int scb_lanczos_bound(int B, int b, int steps, const double *alpha, const double *beta2, double factor,
+                      double *out, void *stream);
 /* deterministic pseudo-random block in (-1, 1) */
 int scb_rand_block(int64_t total, uint64_t seed, double *X, void *stream);
 

@@ -101,6 +101,9 @@ SIGNATURES = {
     "scb_deflate": (_I, [_I, _I64, _I, _I, _P, _P, _P, _P]),
     "scb_residual_norms": (_I, [_I, _I64, _I, _P, _P, _P, _P, _P]),
     "scb_transpose_small": (_I, [_I, _P, _P, _P]),
+    "scb_coldot": (_I, [_I, _I64, _I, _P, _P, _P, _P]),
+    "scb_lanczos_axpy": (_I, [_I, _I64, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "scb_lanczos_bound": (_I, [_I, _I, _I, _P, _P, _D, _P, _P]),
     "scb_rand_block": (_I, [_I64, _U64, _P, _P]),
     "scb_eig_full_workspace_bytes": (_SZ, [_I, _I]),
     "scb_eig_full": (_I, [_I, _I, _P, _P, _P, _P, _SZ, _P]),

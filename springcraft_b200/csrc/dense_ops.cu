@@ -425,3 +425,25 @@ extern "C" int scb_rand_block(int64_t total, uint64_t seed, double* X, void* str
     if (!X || total < 1) return SCB_ERR_INVALID;
     return rand_init(total, seed, X, as_stream(stream));
 }
+
+// ---- column-wise Lanczos building blocks (spectrum bound of operators applied by the caller, e.g. the dense
+// row-slab operator): the same kernels the batched sparse solver uses internally
+extern "C" int scb_coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, void* stream) {
+    if (!A || !Bm || !out || B < 1 || N < 1) return SCB_ERR_INVALID;
+    return scb::coldot(B, N, b, A, Bm, out, scb::as_stream(stream));
+}
+
+extern "C" int scb_lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, double* W,
+                                const double* alpha, const double* beta_prev, const double* nrm2, void* stream) {
+    if (!V || B < 1 || N < 1 || mode < 0 || mode > 2) return SCB_ERR_INVALID;
+    if (mode == 0 && (!Vprev || !W || !alpha)) return SCB_ERR_INVALID;
+    if (mode == 1 && (!Vprev || !W || !nrm2)) return SCB_ERR_INVALID;
+    if (mode == 2 && !nrm2) return SCB_ERR_INVALID;
+    return scb::lanczos_axpy(B, N, b, mode, V, Vprev, W, alpha, beta_prev, nrm2, scb::as_stream(stream));
+}
+
+extern "C" int scb_lanczos_bound(int B, int b, int steps, const double* alpha, const double* beta2, double factor,
+                                 double* out, void* stream) {
+    if (!alpha || !beta2 || !out || B < 1 || steps < 1 || steps > 64) return SCB_ERR_INVALID;
+    return scb::lanczos_bound_plain(B, b, steps, alpha, beta2, factor, out, scb::as_stream(stream));
+}

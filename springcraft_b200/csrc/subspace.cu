@@ -736,7 +736,8 @@ lanczos_axpy_kernel(int64_t N, int mode, double* __restrict__ V, double* __restr
 // largest eigenvalue of each column's k x k Lanczos tridiagonal (bisection on the
 // Sturm count), max over columns -> tightened upper bound in the solver state
 __global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restrict__ alpha,
-                                     const double* __restrict__ beta2, EigState* st, double ub_factor) {
+                                     const double* __restrict__ beta2, EigState* st, double ub_factor,
+                                     double* __restrict__ plain_out) {
     // alpha[j][s][c], beta2[j][s][c] = beta_j^2 (coupling between steps j and j+1)
     const int s = blockIdx.x;
     const int c = threadIdx.x;
@@ -772,6 +773,7 @@ __global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restri
     if (c == 0) {
         double m = 0.0;
         for (int q = 0; q < b; ++q) m = fmax(m, best[q]);
+        if (plain_out) { plain_out[s] = ub_factor * m; return; }
         EigState e = st[s];
         const double est = ub_factor * m;
         if (est > 0.0 && est < e.ub) e.ub = est;
@@ -780,13 +782,14 @@ __global__ void lanczos_bound_kernel(int B, int b, int k, const double* __restri
 }
 
 int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st) {
-    if (b != 32 && b != 64) return SCB_ERR_UNSUPPORTED;
+    if (b != 32 && b != 64 && b != 128) return SCB_ERR_UNSUPPORTED;
     const int chunks = (int)ceil_div(N, kGramRows);
     dim3 grid((unsigned)chunks, (unsigned)B);
     double* part = out;
     if (chunks > 1) SCB_TRY(pool_alloc((void**)&part, sizeof(double) * (size_t)B * chunks * b, st));
     if (b == 32) coldot_kernel<1><<<grid, 256, 0, st>>>(N, A, Bm, part);
-    else coldot_kernel<2><<<grid, 256, 0, st>>>(N, A, Bm, part);
+    else if (b == 64) coldot_kernel<2><<<grid, 256, 0, st>>>(N, A, Bm, part);
+    else coldot_kernel<4><<<grid, 256, 0, st>>>(N, A, Bm, part);
     SCB_LAUNCH_CHECK();
     if (chunks > 1) {
         const int status = sum_chunks(B, b, chunks, part, out, nullptr, st);
@@ -801,6 +804,7 @@ int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, do
     dim3 grid((unsigned)ceil_div(N, kGramRows), (unsigned)B);
     if (b == 32) lanczos_axpy_kernel<1><<<grid, 256, 0, st>>>(N, mode, V, Vprev, W, alpha, beta_prev, nrm2);
     else if (b == 64) lanczos_axpy_kernel<2><<<grid, 256, 0, st>>>(N, mode, V, Vprev, W, alpha, beta_prev, nrm2);
+    else if (b == 128) lanczos_axpy_kernel<4><<<grid, 256, 0, st>>>(N, mode, V, Vprev, W, alpha, beta_prev, nrm2);
     else return SCB_ERR_UNSUPPORTED;
     SCB_LAUNCH_CHECK();
     return SCB_OK;
@@ -809,7 +813,15 @@ int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, do
 int lanczos_bound(int B, int b, int k, const double* alpha, const double* beta2, EigState* state, cudaStream_t st) {
     double ub_factor = 1.03;
     if (const char* env = getenv("SCB_UBFACTOR")) ub_factor = atof(env) > 1.0 ? atof(env) : ub_factor;
-    lanczos_bound_kernel<<<B, 128, 0, st>>>(B, b, k, alpha, beta2, state, ub_factor);
+    lanczos_bound_kernel<<<B, 128, 0, st>>>(B, b, k, alpha, beta2, state, ub_factor, nullptr);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+int lanczos_bound_plain(int B, int b, int k, const double* alpha, const double* beta2, double factor, double* out,
+                        cudaStream_t st) {
+    if (b > 128) return SCB_ERR_UNSUPPORTED;
+    lanczos_bound_kernel<<<B, 128, 0, st>>>(B, b, k, alpha, beta2, nullptr, factor, out);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }

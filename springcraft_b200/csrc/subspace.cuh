@@ -53,6 +53,8 @@ int rand_init(int64_t total, uint64_t seed, double* X, cudaStream_t s);
 int coldot(int B, int64_t N, int b, const double* A, const double* Bm, double* out, cudaStream_t st);
 int lanczos_axpy(int B, int64_t N, int b, int mode, double* V, double* Vprev, double* W, const double* alpha,
                  const double* beta_prev, const double* nrm2, cudaStream_t st);
+int lanczos_bound_plain(int B, int b, int k, const double* alpha, const double* beta2, double factor, double* out,
+                        cudaStream_t st);
 int lanczos_bound(int B, int b, int k, const double* alpha, const double* beta2, EigState* state, cudaStream_t st);
 // FP64 tensor-core versions for 32-column blocks (tallskinny_dmma.cu): S = X^T X and T = X^T HX in one pass;
 // X <- X C, HX <- HX C fused with the squared residual norms of the rotated pairs

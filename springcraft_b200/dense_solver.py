@@ -220,7 +220,42 @@ class DenseRowOperator:
         return Z[0]
 
 
-def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200):
+def lanczos_bound(op, start, steps=8, factor=1.03):
+    """Estimate of the largest eigenvalue from `steps` steps of column-wise Lanczos on the (random) block `start`
+    (every column an independent run), times a safety factor: the Gershgorin bound of an all-pairs Hessian is
+    ~3x too large, which costs ~1.7x more filter steps.  Collective when the operator is partitioned."""
+    torch = _torch()
+    h, st = op.handle, _lib.stream_ptr
+    N, b = int(start.shape[0]), int(start.shape[1])
+    f64 = dict(dtype=torch.float64, device="cuda")
+    V = start.clone()
+    Vp = torch.zeros_like(V)
+    alpha = torch.zeros((steps, b), **f64)
+    beta2 = torch.zeros((steps, b), **f64)
+    nrm = torch.empty(b, **f64)
+    _lib.check(h.scb_coldot(1, N, b, _lib.ptr(V), _lib.ptr(V), _lib.ptr(nrm), st()))
+    _lib.check(h.scb_lanczos_axpy(1, N, b, 2, _lib.ptr(V), None, None, None, None, _lib.ptr(nrm), st()))
+    for j in range(steps):
+        W = op.apply(V)
+        if W.data_ptr() == V.data_ptr():
+            raise RuntimeError("operator returned its input block")
+        W = W if op.world == 1 else W.clone()      # peer-pool blocks rotate: keep this one
+        _lib.check(h.scb_coldot(1, N, b, _lib.ptr(V), _lib.ptr(W), _lib.ptr(alpha[j]), st()))
+        _lib.check(h.scb_lanczos_axpy(1, N, b, 0, _lib.ptr(V), _lib.ptr(Vp), _lib.ptr(W), _lib.ptr(alpha[j]),
+                                      _lib.ptr(beta2[j - 1]) if j else None, None, st()))
+        _lib.check(h.scb_coldot(1, N, b, _lib.ptr(W), _lib.ptr(W), _lib.ptr(beta2[j]), st()))
+        if j + 1 < steps:
+            _lib.check(h.scb_lanczos_axpy(1, N, b, 1, _lib.ptr(V), _lib.ptr(Vp), _lib.ptr(W), None, None,
+                                          _lib.ptr(beta2[j]), st()))
+    out = torch.empty(1, **f64)
+    _lib.check(h.scb_lanczos_bound(1, b, steps, _lib.ptr(alpha), _lib.ptr(beta2), float(factor), _lib.ptr(out), st()))
+    if op.world > 1:
+        import torch.distributed as dist
+        dist.broadcast(out, src=0)                 # one value for every rank
+    return float(out.item())
+
+
+def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200, lanczos_steps=8):
     """The k lowest modes of the operator deflated by Z ([N][nz], orthonormal): returns
     (theta[b], X[N][b], resid[b], outer_iterations).  Columns 0..k-1 are converged to
     ``||H x - theta x|| <= tol * theta_k``."""
@@ -242,7 +277,8 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
     Cm = torch.empty((b, b), **f64)
     rn2 = torch.empty(b, **f64)
     _lib.check(h.scb_rand_block(N * b, seed, _lib.ptr(A), st()))
-    ub = op.spectrum_bound() * (1.0 + 1e-10)
+    ub_safe = op.spectrum_bound() * (1.0 + 1e-10)
+    ub = min(ub_safe, lanczos_bound(op, A, steps=lanczos_steps)) if lanczos_steps else ub_safe
     theta = None
     lo = a0 = 0.0
     cur = A
@@ -285,6 +321,9 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
         th = theta.cpu().numpy()
         res = np.sqrt(np.maximum(rn2.cpu().numpy(), 0.0))
         a0 = float(th[0])
+        if outer > 0 and ub < ub_safe and th[b - 1] > 0.5 * ub:
+            # a filtered block must sit far below the bound: the Lanczos estimate was too small, repair it
+            ub = min(ub_safe, 1.15 * max(ub, float(th[b - 1])))
         lo = min(float(th[b - 1]), 0.98 * ub)
         if not lo > a0:
             lo = a0 + 0.5 * (ub - a0)
