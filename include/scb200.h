@@ -237,6 +237,27 @@ int scb_residual_norms(int B, int64_t N, int b, const double *X, const double *H
                        const double *theta, double *rn2, void *stream);
 /* out = in^T for a b x b matrix (mode rows -> rotation columns) */
 int scb_transpose_small(int b, const double *in, double *out, void *stream);
+/* ---- residual-form Chebyshev filter of the dense row-slab operator on the TF32 tensor cores (dense_tf32.cu).
+ * For a Ritz pair (theta, x) with r = Hx - theta x the filtered vector is x + z, z = q(H) r / p(theta); z is
+ * proportional to the residual, so it may be computed with a single-precision (TF32) copy of the slab while H X,
+ * Rayleigh-Ritz and the residuals stay FP64.  Blocks of the filter are FP32 and TRANSPOSED: zT[b][ld],
+ * ld = scb_tf32_ld(N) (N rounded up to a multiple of 4), b = 128.
+ *   scb_dense_slab_to_f32:     slab32[rows][ld] <- slab[rows][N]
+ *   scb_resform_prepare:       rhatT = ((HX - X theta') / |r|)^T with theta' = min(theta, lo), z1T (first filter step),
+ *                              z0T = 0 and the per-column coefficient tables cA, cB [deg][b] of steps 1..deg-1
+ *   scb_dense_slab_tf32_apply: rows [row0,row1) of  outT = cA (H zcur - cshift zcur + rhat) - cB zprev  (fused != 0,
+ *                              cA/cB = the step's row of the tables, cshift = (ub+lo)/2; outT may alias zprevT) or
+ *                              outT = H zcur (fused == 0); tcgen05.mma kind::tf32, TMA operands, TMEM accumulator
+ *   scb_resform_finish:        X[N][b] += |r| z^T */
+int64_t scb_tf32_ld(int64_t N);
+int scb_dense_slab_to_f32(int64_t N, int64_t rows, const double *slab, float *slab32, void *stream);
+int scb_resform_prepare(int64_t N, int b, int deg, const double *X, const double *HX, const double *theta,
+                        const double *rn2, double lo, double ub, float *rhatT, float *z1T, float *z0T,
+                        float *cA, float *cB, void *stream);
+int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float *slab32, int b,
+                              const float *zcurT, const float *zprevT, const float *rhatT, float *outT,
+                              const float *cA, const float *cB, double cshift, int fused, void *stream);
+int scb_resform_finish(int64_t N, int b, const double *rn2, const float *zT, double *X, void *stream);
 /* Column-wise Lanczos (every column of a block is an independent Lanczos run; spectrum bound of an operator the
  * caller applies, e.g. the dense row-slab operator).  b = 32, 64 or 128.
  *   scb_coldot:        out[B][b] = column-wise dot products of A and Bm ([B][N][b])

@@ -194,6 +194,49 @@ class DenseRowOperator:
         full = gather_results(local.view(self.row1 - self.row0, self.D * b), self.n, dim=0)
         return full.view(self.N, b)
 
+    # -- residual-form filter on the TF32 tensor cores -------------------------------
+    def slab32(self):
+        """Single-precision copy of the row slab (built on first use; 4 N^2 / G bytes)."""
+        torch = _torch()
+        if getattr(self, "_slab32", None) is None:
+            ld = int(self.handle.scb_tf32_ld(self.N))
+            out = torch.empty((self.slab.shape[0], ld), dtype=torch.float32, device="cuda")
+            _lib.check(self.handle.scb_dense_slab_to_f32(self.N, self.slab.shape[0], _lib.ptr(self.slab),
+                                                         _lib.ptr(out), _lib.stream_ptr()))
+            self._slab32 = out
+        return self._slab32
+
+    def filter_residual_tf32(self, A, HX, theta, rn2, lo, ub, degree):
+        """A <- A + |r| z with z = q(H) r / p(theta) from `degree` Chebyshev steps on [lo, ub] (see dense_tf32.cu);
+        A are Ritz vectors, HX = H A, rn2 their squared residual norms.  One GPU, 128-column blocks."""
+        torch = _torch()
+        h, st = self.handle, _lib.stream_ptr
+        b = int(A.shape[1])
+        if self.world != 1 or b != 128:
+            raise NotImplementedError("the TF32 filter runs on one GPU with 128-column blocks")
+        ld = int(h.scb_tf32_ld(self.N))
+        buf = self._tf32_buffers = getattr(self, "_tf32_buffers", None) or {
+            "z": [torch.empty((b, ld), dtype=torch.float32, device="cuda") for _ in range(3)],
+            "rhat": torch.empty((b, ld), dtype=torch.float32, device="cuda"),
+            "cA": torch.empty((64, b), dtype=torch.float32, device="cuda"),
+            "cB": torch.empty((64, b), dtype=torch.float32, device="cuda")}
+        degree = int(min(max(degree, 2), 64))
+        zprev, zcur, znext = buf["z"]
+        slab32 = self.slab32()
+        _lib.check(h.scb_resform_prepare(self.N, b, degree, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(theta), _lib.ptr(rn2),
+                                         float(lo), float(ub), _lib.ptr(buf["rhat"]), _lib.ptr(zcur), _lib.ptr(zprev),
+                                         _lib.ptr(buf["cA"]), _lib.ptr(buf["cB"]), st()))
+        cshift = 0.5 * (ub + lo)
+        for k in range(1, degree):
+            # z_{k+1} overwrites z_{k-1}
+            _lib.check(h.scb_dense_slab_tf32_apply(self.N, 0, self.N, _lib.ptr(slab32), b, _lib.ptr(zcur),
+                                                   _lib.ptr(zprev), _lib.ptr(buf["rhat"]), _lib.ptr(zprev),
+                                                   _lib.ptr(buf["cA"][k]), _lib.ptr(buf["cB"][k]), cshift, 1, st()))
+            zprev, zcur = zcur, zprev
+        _lib.check(h.scb_resform_finish(self.N, b, _lib.ptr(rn2), _lib.ptr(zcur), _lib.ptr(A), st()))
+        del znext
+        return A
+
     def close(self):
         """Release the peer-mapped blocks (collective; tensors returned by `apply` die with them)."""
         for pool in self._pools.values():
@@ -255,18 +298,28 @@ def lanczos_bound(op, start, steps=8, factor=1.03):
     return float(out.item())
 
 
-def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200, lanczos_steps=8):
+def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200, lanczos_steps=8,
+                     filter=None):
     """The k lowest modes of the operator deflated by Z ([N][nz], orthonormal): returns
     (theta[b], X[N][b], resid[b], outer_iterations).  Columns 0..k-1 are converged to
-    ``||H x - theta x|| <= tol * theta_k``."""
+    ``||H x - theta x|| <= tol * theta_k``.
+
+    ``filter``: "fp64" = Chebyshev filter of the block itself with the FP64 slab kernel; "tf32" = residual-form
+    filter (the correction of every Ritz pair) on the TF32 tensor cores, FP64 everywhere else -- one GPU, 128-column
+    blocks (default there; ``SCB_DENSE_FILTER`` overrides)."""
     torch = _torch()
     h = op.handle
     st = _lib.stream_ptr
     N = op.N
+    filter = filter or os.environ.get("SCB_DENSE_FILTER") or ("tf32" if op.world == 1 else "fp64")
+    if filter not in ("fp64", "tf32"):
+        raise ValueError("filter must be 'fp64' or 'tf32'")
     if b is None:
-        b = 64 if k + 8 <= 64 else 128
+        b = 128 if (filter == "tf32" or k + 8 > 64) else 64
     if k > b or b not in (64, 128):
         raise NotImplementedError(f"k={k} needs a block wider than 128 columns")
+    if filter == "tf32" and (op.world != 1 or b != 128):
+        filter = "fp64"
     nz = 0 if Z is None else int(Z.shape[1])
     if N < b + nz:
         raise NotImplementedError("system smaller than the solver block: use the full-spectrum solver")
@@ -289,7 +342,10 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
         _lib.check(h.scb_rotate(1, N, b, _lib.ptr(Cm), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(also), _lib.ptr(also), st()))
 
     for outer in range(max_outer + 1):
-        if outer > 0:
+        if outer > 0 and filter == "tf32":
+            op.filter_residual_tf32(A, HX, theta, rn2, lo, ub, degree)   # A <- A + correction (nearly orthonormal)
+            cur = A
+        elif outer > 0:
             half, c = 0.5 * (ub - lo), 0.5 * (ub + lo)
             sigma1 = half / (a0 - c)
             sigma = sigma1
@@ -302,7 +358,8 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
             cur = curb
         if nz:
             _lib.check(h.scb_deflate(1, N, b, nz, _lib.ptr(Z), _lib.ptr(cur), _lib.ptr(scratch), st()))
-        orthonormalise(cur, A)
+        if not (outer > 0 and filter == "tf32"):
+            orthonormalise(cur, A)      # the residual-form update keeps A well conditioned: CholQR below suffices
         HX = op.apply(A)
         orthonormalise(A, A, also=HX)          # second pass (CholQR2); H (A C) = (H A) C
         _lib.check(h.scb_gram(1, N, b, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(G), st()))
