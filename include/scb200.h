@@ -250,14 +250,15 @@ int scb_transpose_small(int b, const double *in, double *out, void *stream);
  *                              outT = H zcur (fused == 0); tcgen05.mma kind::tf32, TMA operands, TMEM accumulator
  *   scb_resform_finish:        X[N][b] += |r| z^T */
 int64_t scb_tf32_ld(int64_t N);
-int scb_dense_slab_to_f32(int64_t N, int64_t rows, const double *slab, float *slab32, void *stream);
+int scb_dense_slab_to_f32(int64_t N, int64_t rows, const double *slab, float *slab32, float *slab32_lo,
+                          void *stream);
 int scb_resform_prepare(int64_t N, int b, int deg, const double *X, const double *HX, const double *theta,
                         const double *rn2, double lo, double ub, float *rhatT, float *z1T, float *z0T,
-                        float *cA, float *cB, void *stream);
-int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float *slab32, int b,
-                              const float *zcurT, const float *zprevT, const float *rhatT, float *outT,
+                        float *cA, float *cB, int split, void *stream);
+int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float *slab32, const float *slab32_lo,
+                              int b, const float *zcurT, const float *zprevT, const float *rhatT, float *outT,
                               const float *cA, const float *cB, double cshift, int fused, void *stream);
-int scb_resform_finish(int64_t N, int b, const double *rn2, const float *zT, double *X, void *stream);
+int scb_resform_finish(int64_t N, int b, const double *rn2, const float *zT, double *X, int split, void *stream);
 /* Column-wise Lanczos (every column of a block is an independent Lanczos run; spectrum bound of an operator the
  * caller applies, e.g. the dense row-slab operator).  b = 32, 64 or 128.
  *   scb_coldot:        out[B][b] = column-wise dot products of A and Bm ([B][N][b])

@@ -35,3 +35,25 @@ exchange = op.exchange
 op.close()                 # collective: releases the peer-mapped blocks
 if int(os.environ.get("WORLD_SIZE","1"))>1: dist.destroy_process_group()
 if int(os.environ.get("RANK","0"))==0: print(f"lowest {k} modes: {elapsed:.2f} s, {iters} outer iterations, ub={ub:.1f}, theta[0]={theta[0].item():.4g}, theta[k-1]={theta[k-1].item():.4g}, maxres={res[:k].max().item():.2e}")
+# ---- the same solve with the FP64 filter, and one TF32 filter step timed alone
+if int(os.environ.get("WORLD_SIZE","1")) == 1 and os.environ.get("C4_COMPARE", "1") == "1":
+    op = DenseRowOperator(coord, sc.ParameterFreeForceField(), 3)
+    from springcraft_b200 import _lib
+    h = _lib.require_device()
+    ld = int(h.scb_tf32_ld(op.N)); s32, s32lo = op.slab32(True)
+    Zc = torch.randn((256, ld), dtype=torch.float32, device="cuda"); Zp = torch.randn_like(Zc); Rh = torch.randn((128, ld), dtype=torch.float32, device="cuda")
+    cA = torch.rand(128, device="cuda") * 0.1; cB = torch.rand(128, device="cuda")
+    def step():
+        _lib.check(h.scb_dense_slab_tf32_apply(op.N, 0, op.N, _lib.ptr(s32), _lib.ptr(s32lo), 128, _lib.ptr(Zc), _lib.ptr(Zp), _lib.ptr(Rh), _lib.ptr(Zp), _lib.ptr(cA), _lib.ptr(cB), 0.7, 1, _lib.stream_ptr()))
+    for _ in range(3): step()
+    torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): step()
+    e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1)/10
+    print(f"3xTF32 filter step (tcgen05): {ms:.3f} ms = {3*2*op.N**2*128/ms/1e9:.0f} TFLOP/s issued, slab stream {2*s32.numel()*4/ms/1e6:.0f} GB/s")
+    Z = op.rigid_basis()
+    torch.cuda.synchronize(); t=time.perf_counter()
+    theta, A, res, iters = eig_lowest_dense(op, k, Z=Z, filter="fp64")
+    torch.cuda.synchronize()
+    print(f"FP64 filter: lowest {k} modes: {time.perf_counter()-t:.2f} s, {iters} outer iterations")
+    op.close()

@@ -102,10 +102,10 @@ SIGNATURES = {
     "scb_residual_norms": (_I, [_I, _I64, _I, _P, _P, _P, _P, _P]),
     "scb_transpose_small": (_I, [_I, _P, _P, _P]),
     "scb_tf32_ld": (_I64, [_I64]),
-    "scb_dense_slab_to_f32": (_I, [_I64, _I64, _P, _P, _P]),
-    "scb_resform_prepare": (_I, [_I64, _I, _I, _P, _P, _P, _P, _D, _D, _P, _P, _P, _P, _P, _P]),
-    "scb_dense_slab_tf32_apply": (_I, [_I64, _I64, _I64, _P, _I, _P, _P, _P, _P, _P, _P, _D, _I, _P]),
-    "scb_resform_finish": (_I, [_I64, _I, _P, _P, _P, _P]),
+    "scb_dense_slab_to_f32": (_I, [_I64, _I64, _P, _P, _P, _P]),
+    "scb_resform_prepare": (_I, [_I64, _I, _I, _P, _P, _P, _P, _D, _D, _P, _P, _P, _P, _P, _I, _P]),
+    "scb_dense_slab_tf32_apply": (_I, [_I64, _I64, _I64, _P, _P, _I, _P, _P, _P, _P, _P, _P, _D, _I, _P]),
+    "scb_resform_finish": (_I, [_I64, _I, _P, _P, _P, _I, _P]),
     "scb_coldot": (_I, [_I, _I64, _I, _P, _P, _P, _P]),
     "scb_lanczos_axpy": (_I, [_I, _I64, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "scb_lanczos_bound": (_I, [_I, _I, _I, _P, _P, _D, _P, _P]),

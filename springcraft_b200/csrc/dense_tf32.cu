@@ -12,6 +12,12 @@
 // Blocks are kept TRANSPOSED ([b][ld], the long dimension contiguous): that is the K-major B operand of the MMA and
 // makes the epilogue's global accesses coalesced (TMEM lane = matrix row = consecutive addresses across a warp).
 //
+// Precision: a single TF32 product (10-bit mantissa) is not enough at full size -- with 60,000 closely spaced
+// eigenvalues the error of the correction (~eps_tf32 |H| / gap) is O(1) and the solver needs 28 outer iterations
+// instead of 9.  The kernel therefore evaluates the 3-term split product  H_hi z_hi + H_hi z_lo + H_lo z_hi  (hi = the
+// TF32-representable part, lo = the remainder; FP32-class accuracy, "3xTF32"): two slab streams per step instead of
+// one, still ~6x faster than the FP64 product.  SPLIT = 1 keeps the single product (tests, small systems).
+//
 // Kernel: one CTA per 128-row tile of the slab, 128 x b accumulator (b = 128) in TMEM.
 //   warp 0   TMA producer: A tile 128 x 32 floats of the slab + B tile b x 32 floats of Zcur^T per stage, 128B swizzle
 //   warp 1   TMEM allocation; one elected lane issues 4 x tcgen05.mma (K = 8 each) per stage, tcgen05.commit frees it
@@ -25,9 +31,9 @@ namespace scb {
 constexpr int kT32BM = 128;        // rows per CTA (UMMA M)
 constexpr int kT32BN = 128;        // block columns (UMMA N)
 constexpr int kT32BK = 32;         // floats per stage along K = one 128-byte swizzle row
-constexpr int kT32Stages = 3;      // 32 KB per stage; 2 CTAs per SM keep ~192 KB of slab in flight per SM
+constexpr int kT32Stages = 3;      // SPLIT 1: 32 KB per stage, 2 CTAs per SM; SPLIT 3: 64 KB per stage, 1 CTA per SM
 constexpr int kT32Threads = 192;
-constexpr uint32_t kT32StageBytes = (kT32BM + kT32BN) * kT32BK * 4;
+constexpr uint32_t kT32TileBytes = kT32BM * kT32BK * 4;   // one 128 x 32 fp32 operand tile (A or B)
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -97,6 +103,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 struct T32Epilogue {
+    // SPLIT 3: every z block is [2 b][ld], rows 0..b-1 the TF32-representable part, rows b..2b-1 the remainder
     const float* zcur;     // [b][ld]  Zcur^T   (NULL: plain product, out = H Z)
     const float* zprev;    // [b][ld]  Zprev^T
     const float* rhat;     // [b][ld]  normalised residual, transposed
@@ -109,9 +116,14 @@ struct T32Epilogue {
     int rows;              // rows of the slab
 };
 
-__global__ void __launch_bounds__(kT32Threads, 2)
-dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int K,
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+template <int SPLIT>
+__global__ void __launch_bounds__(kT32Threads, SPLIT == 1 ? 2 : 1)
+dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                       const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo, int K,
                        T32Epilogue ep) {
+    constexpr uint32_t kT32StageBytes = (SPLIT == 1 ? 2 : 4) * kT32TileBytes;
     extern __shared__ __align__(1024) uint8_t t32_smem[];
     __shared__ uint64_t full_bar[kT32Stages], empty_bar[kT32Stages], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -145,10 +157,14 @@ dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 const uint32_t ph = (kb / kT32Stages) & 1;
                 mb_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a = tiles + (size_t)s * kT32StageBytes;
-                uint8_t* b = a + kT32BM * kT32BK * 4;
+                uint8_t* b = a + kT32TileBytes;
                 mb_expect_tx(&full_bar[s], kT32StageBytes);
                 tma_load_2d(a, &mapA, &full_bar[s], kb * kT32BK, m0);
                 tma_load_2d(b, &mapB, &full_bar[s], kb * kT32BK, 0);
+                if (SPLIT == 3) {
+                    tma_load_2d(b + kT32TileBytes, &mapAlo, &full_bar[s], kb * kT32BK, m0);
+                    tma_load_2d(b + 2 * kT32TileBytes, &mapBlo, &full_bar[s], kb * kT32BK, 0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -160,11 +176,20 @@ dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 mb_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = s32(tiles + (size_t)s * kT32StageBytes);
-                const uint32_t b_addr = a_addr + kT32BM * kT32BK * 4;
+                const uint32_t b_addr = a_addr + kT32TileBytes;
                 const uint64_t adesc = umma_desc_k128(a_addr), bdesc = umma_desc_k128(b_addr);
 #pragma unroll
                 for (int k = 0; k < kT32BK / 8; ++k)   // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
                     umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, (kb > 0 || k > 0) ? 1u : 0u);
+                if (SPLIT == 3) {
+                    const uint64_t alo = umma_desc_k128(b_addr + kT32TileBytes);
+                    const uint64_t blo = umma_desc_k128(b_addr + 2 * kT32TileBytes);
+#pragma unroll
+                    for (int k = 0; k < kT32BK / 8; ++k) {
+                        umma_tf32(tmem_base, adesc + 2 * k, blo + 2 * k, 1u);     // H_hi z_lo
+                        umma_tf32(tmem_base, alo + 2 * k, bdesc + 2 * k, 1u);     // H_lo z_hi
+                    }
+                }
                 umma_commit(&empty_bar[s]);            // frees the stage once these MMAs have read it
             }
             umma_commit(&tmem_full_bar);               // accumulator complete
@@ -187,11 +212,19 @@ dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 const int n = 32 * c + j;
                 const int64_t idx = (int64_t)n * ep.ld + col;
                 float v = acc[j];
+                const int64_t lo_off = (int64_t)kT32BN * ep.ld;     // SPLIT 3: the remainder rows of a block
                 if (ep.zcur) {
-                    const float zc = ep.zcur[idx], zp = ep.zprev[idx], rh = ep.rhat[idx];
-                    v = ep.cA[n] * (fmaf(-ep.cshift, zc, v) + rh) - ep.cB[n] * zp;
+                    float zc = ep.zcur[idx], zp = ep.zprev[idx];
+                    if (SPLIT == 3) { zc += ep.zcur[idx + lo_off]; zp += ep.zprev[idx + lo_off]; }
+                    v = ep.cA[n] * (fmaf(-ep.cshift, zc, v) + ep.rhat[idx]) - ep.cB[n] * zp;
                 }
-                ep.out[idx] = v;
+                if (SPLIT == 3) {
+                    const float hi = tf32_hi(v);
+                    ep.out[idx] = hi;
+                    ep.out[idx + lo_off] = v - hi;
+                } else {
+                    ep.out[idx] = v;
+                }
             }
         }
     }
@@ -205,11 +238,21 @@ dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 
 // ---- helpers around the filter ----------------------------------------------------------------------------
 // FP64 row-major slab -> FP32 with a padded leading dimension (TMA needs 16-byte multiples)
+// out_lo == NULL: plain cast; else out = the TF32-representable part, out_lo = the remainder (from the FP64 value)
 __global__ void __launch_bounds__(256)
-slab_to_f32_kernel(int64_t rows, int64_t N, int64_t ld, const double* __restrict__ in, float* __restrict__ out) {
+slab_to_f32_kernel(int64_t rows, int64_t N, int64_t ld, const double* __restrict__ in, float* __restrict__ out,
+                   float* __restrict__ out_lo) {
     const int64_t r = blockIdx.y;
-    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < ld; c += (int64_t)gridDim.x * 256)
-        out[r * ld + c] = c < N ? (float)in[r * N + c] : 0.f;
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < ld; c += (int64_t)gridDim.x * 256) {
+        const double v = c < N ? in[r * N + c] : 0.0;
+        if (out_lo) {
+            const float hi = tf32_hi((float)v);
+            out[r * ld + c] = hi;
+            out_lo[r * ld + c] = (float)(v - (double)hi);
+        } else {
+            out[r * ld + c] = (float)v;
+        }
+    }
 }
 
 // residual form, start of a filter: R = HX - X theta' (theta' = min(theta, lo)), normalised per column;
@@ -217,7 +260,7 @@ slab_to_f32_kernel(int64_t rows, int64_t N, int64_t ld, const double* __restrict
 __global__ void __launch_bounds__(256)
 resform_prepare_kernel(int64_t N, int b, int64_t ld, const double* __restrict__ X, const double* __restrict__ HX,
                        const double* __restrict__ theta, const double* __restrict__ rn2, double lo, double ub,
-                       float* __restrict__ rhatT, float* __restrict__ z1T, float* __restrict__ z0T) {
+                       float* __restrict__ rhatT, float* __restrict__ z1T, float* __restrict__ z0T, int split) {
     __shared__ float tile[32][33];
     const double ehalf = 0.5 * (ub - lo), cmid = 0.5 * (ub + lo);
     const int64_t r0 = (int64_t)blockIdx.x * 32;
@@ -244,8 +287,17 @@ resform_prepare_kernel(int64_t N, int b, int64_t ld, const double* __restrict__ 
             const double x = (fmin(theta[c], lo) - cmid) / ehalf;
             const int64_t idx = (int64_t)c * ld + r;
             rhatT[idx] = v;
-            z1T[idx] = (float)((double)v / (x * ehalf));
+            const float z1 = (float)((double)v / (x * ehalf));
             z0T[idx] = 0.f;
+            if (split) {                             // [2 b][ld]: TF32-representable part, then the remainder
+                const float hi = tf32_hi(z1);
+                const int64_t lo_off = (int64_t)b * ld;
+                z1T[idx] = hi;
+                z1T[idx + lo_off] = z1 - hi;
+                z0T[idx + lo_off] = 0.f;
+            } else {
+                z1T[idx] = z1;
+            }
         }
     }
 }
@@ -268,14 +320,16 @@ __global__ void resform_coef_kernel(int b, int deg, const double* __restrict__ t
 // X[m][n] += |r_n| * zT[n][m]
 __global__ void __launch_bounds__(256)
 resform_finish_kernel(int64_t N, int b, int64_t ld, const double* __restrict__ rn2, const float* __restrict__ zT,
-                      double* __restrict__ X) {
+                      double* __restrict__ X, int split) {
     __shared__ float tile[32][33];
     const int64_t r0 = (int64_t)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
         const int64_t r = r0 + tx;
-        tile[i][tx] = r < N ? zT[(int64_t)(c0 + i) * ld + r] : 0.f;
+        float z = r < N ? zT[(int64_t)(c0 + i) * ld + r] : 0.f;
+        if (split && r < N) z += zT[(int64_t)(b + c0 + i) * ld + r];
+        tile[i][tx] = z;
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -321,56 +375,69 @@ using namespace scb;
 
 extern "C" int64_t scb_tf32_ld(int64_t N) { return (N + 3) & ~(int64_t)3; }
 
-extern "C" int scb_dense_slab_to_f32(int64_t N, int64_t rows, const double* slab, float* slab32, void* stream) {
+extern "C" int scb_dense_slab_to_f32(int64_t N, int64_t rows, const double* slab, float* slab32, float* slab32_lo,
+                                     void* stream) {
     if (!slab || !slab32 || N < 1 || rows < 1) return SCB_ERR_INVALID;
     const int64_t ld = scb_tf32_ld(N);
     dim3 grid((unsigned)ceil_div(ld, 256 * 8), (unsigned)rows);
-    slab_to_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, N, ld, slab, slab32);
+    slab_to_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, N, ld, slab, slab32, slab32_lo);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
 
 extern "C" int scb_resform_prepare(int64_t N, int b, int deg, const double* X, const double* HX, const double* theta,
                                    const double* rn2, double lo, double ub, float* rhatT, float* z1T, float* z0T,
-                                   float* cA, float* cB, void* stream) {
+                                   float* cA, float* cB, int split, void* stream) {
     if (!X || !HX || !theta || !rn2 || !rhatT || !z1T || !z0T || !cA || !cB) return SCB_ERR_INVALID;
     if (b % 32 != 0 || deg < 2 || !(ub > lo)) return SCB_ERR_INVALID;
     const int64_t ld = scb_tf32_ld(N);
     cudaStream_t st = as_stream(stream);
     dim3 grid((unsigned)ceil_div(ld, 32), (unsigned)(b / 32));
-    resform_prepare_kernel<<<grid, 256, 0, st>>>(N, b, ld, X, HX, theta, rn2, lo, ub, rhatT, z1T, z0T);
+    resform_prepare_kernel<<<grid, 256, 0, st>>>(N, b, ld, X, HX, theta, rn2, lo, ub, rhatT, z1T, z0T, split);
     SCB_LAUNCH_CHECK();
     resform_coef_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, st>>>(b, deg, theta, lo, ub, cA, cB);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
 
-extern "C" int scb_resform_finish(int64_t N, int b, const double* rn2, const float* zT, double* X, void* stream) {
+extern "C" int scb_resform_finish(int64_t N, int b, const double* rn2, const float* zT, double* X, int split,
+                                  void* stream) {
     if (!rn2 || !zT || !X || b % 32 != 0) return SCB_ERR_INVALID;
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)(b / 32));
-    resform_finish_kernel<<<grid, 256, 0, as_stream(stream)>>>(N, b, scb_tf32_ld(N), rn2, zT, X);
+    resform_finish_kernel<<<grid, 256, 0, as_stream(stream)>>>(N, b, scb_tf32_ld(N), rn2, zT, X, split);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }
 
-extern "C" int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float* slab32, int b,
-                                         const float* zcurT, const float* zprevT, const float* rhatT, float* outT,
-                                         const float* cA, const float* cB, double cshift, int fused, void* stream) {
+extern "C" int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float* slab32,
+                                         const float* slab32_lo, int b, const float* zcurT, const float* zprevT,
+                                         const float* rhatT, float* outT, const float* cA, const float* cB,
+                                         double cshift, int fused, void* stream) {
     if (!slab32 || !zcurT || !outT || N < 1 || row0 < 0 || row1 <= row0 || row1 > N) return SCB_ERR_INVALID;
     if (b != kT32BN) return SCB_ERR_UNSUPPORTED;
     if (fused && (!zprevT || !rhatT || !cA || !cB)) return SCB_ERR_INVALID;
     const int64_t ld = scb_tf32_ld(N);
     const int64_t rows = row1 - row0;
-    CUtensorMap mapA, mapB;
+    const bool split = slab32_lo != nullptr;    // z blocks are then [2 b][ld] (hi rows, lo rows)
+    CUtensorMap mapA, mapB, mapAlo, mapBlo;
     SCB_TRY(make_map(&mapA, slab32, N, rows, ld, kT32BM));
     SCB_TRY(make_map(&mapB, zcurT, N, b, ld, kT32BN));
+    SCB_TRY(make_map(&mapAlo, split ? slab32_lo : slab32, N, rows, ld, kT32BM));
+    SCB_TRY(make_map(&mapBlo, split ? zcurT + (int64_t)b * ld : zcurT, N, b, ld, kT32BN));
     T32Epilogue ep;
     ep.zcur = fused ? zcurT : nullptr; ep.zprev = zprevT; ep.rhat = rhatT; ep.out = outT;
     ep.cA = cA; ep.cB = cB; ep.cshift = (float)cshift; ep.ld = ld; ep.row0 = (int)row0; ep.rows = (int)rows;
-    const size_t smem = (size_t)kT32Stages * kT32StageBytes + 1024;
-    SCB_CUDA(cudaFuncSetAttribute(dense_slab_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_slab_tf32_kernel<<<(unsigned)ceil_div(rows, kT32BM), kT32Threads, smem, as_stream(stream)>>>(mapA, mapB, (int)N,
-                                                                                                      ep);
+    const unsigned grid = (unsigned)ceil_div(rows, kT32BM);
+    cudaStream_t st = as_stream(stream);
+    if (split) {
+        const size_t smem = (size_t)kT32Stages * 4 * kT32TileBytes + 1024;
+        SCB_CUDA(cudaFuncSetAttribute(dense_slab_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_slab_tf32_kernel<3><<<grid, kT32Threads, smem, st>>>(mapA, mapB, mapAlo, mapBlo, (int)N, ep);
+    } else {
+        const size_t smem = (size_t)kT32Stages * 2 * kT32TileBytes + 1024;
+        SCB_CUDA(cudaFuncSetAttribute(dense_slab_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_slab_tf32_kernel<1><<<grid, kT32Threads, smem, st>>>(mapA, mapB, mapAlo, mapBlo, (int)N, ep);
+    }
     SCB_LAUNCH_CHECK();
     return SCB_OK;
 }

@@ -195,46 +195,54 @@ class DenseRowOperator:
         return full.view(self.N, b)
 
     # -- residual-form filter on the TF32 tensor cores -------------------------------
-    def slab32(self):
-        """Single-precision copy of the row slab (built on first use; 4 N^2 / G bytes)."""
+    def slab32(self, split=True):
+        """Single-precision copy of the row slab (built on first use): with ``split`` the TF32-representable part
+        and the remainder (two slabs, 8 N^2 / G bytes), else one plain FP32 slab."""
         torch = _torch()
-        if getattr(self, "_slab32", None) is None:
+        key = "_slab32_split" if split else "_slab32_plain"
+        if getattr(self, key, None) is None:
             ld = int(self.handle.scb_tf32_ld(self.N))
-            out = torch.empty((self.slab.shape[0], ld), dtype=torch.float32, device="cuda")
+            hi = torch.empty((self.slab.shape[0], ld), dtype=torch.float32, device="cuda")
+            lo = torch.empty_like(hi) if split else None
             _lib.check(self.handle.scb_dense_slab_to_f32(self.N, self.slab.shape[0], _lib.ptr(self.slab),
-                                                         _lib.ptr(out), _lib.stream_ptr()))
-            self._slab32 = out
-        return self._slab32
+                                                         _lib.ptr(hi), _lib.ptr(lo), _lib.stream_ptr()))
+            setattr(self, key, (hi, lo))
+        return getattr(self, key)
 
-    def filter_residual_tf32(self, A, HX, theta, rn2, lo, ub, degree):
+    def filter_residual_tf32(self, A, HX, theta, rn2, lo, ub, degree, split=True):
         """A <- A + |r| z with z = q(H) r / p(theta) from `degree` Chebyshev steps on [lo, ub] (see dense_tf32.cu);
-        A are Ritz vectors, HX = H A, rn2 their squared residual norms.  One GPU, 128-column blocks."""
+        A are Ritz vectors, HX = H A, rn2 their squared residual norms.  One GPU, 128-column blocks.
+        ``split``: 3-term TF32 product (FP32-class accuracy, two slab streams per step) instead of a single one."""
         torch = _torch()
         h, st = self.handle, _lib.stream_ptr
         b = int(A.shape[1])
         if self.world != 1 or b != 128:
             raise NotImplementedError("the TF32 filter runs on one GPU with 128-column blocks")
         ld = int(h.scb_tf32_ld(self.N))
-        buf = self._tf32_buffers = getattr(self, "_tf32_buffers", None) or {
-            "z": [torch.empty((b, ld), dtype=torch.float32, device="cuda") for _ in range(3)],
-            "rhat": torch.empty((b, ld), dtype=torch.float32, device="cuda"),
-            "cA": torch.empty((64, b), dtype=torch.float32, device="cuda"),
-            "cB": torch.empty((64, b), dtype=torch.float32, device="cuda")}
+        rows = 2 * b if split else b
+        cache = getattr(self, "_tf32_buffers", None)
+        if cache is None or cache["rows"] != rows:
+            cache = self._tf32_buffers = {
+                "rows": rows,
+                "z": [torch.empty((rows, ld), dtype=torch.float32, device="cuda") for _ in range(2)],
+                "rhat": torch.empty((b, ld), dtype=torch.float32, device="cuda"),
+                "cA": torch.empty((64, b), dtype=torch.float32, device="cuda"),
+                "cB": torch.empty((64, b), dtype=torch.float32, device="cuda")}
         degree = int(min(max(degree, 2), 64))
-        zprev, zcur, znext = buf["z"]
-        slab32 = self.slab32()
+        zprev, zcur = cache["z"]
+        hi, lo_slab = self.slab32(split)
         _lib.check(h.scb_resform_prepare(self.N, b, degree, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(theta), _lib.ptr(rn2),
-                                         float(lo), float(ub), _lib.ptr(buf["rhat"]), _lib.ptr(zcur), _lib.ptr(zprev),
-                                         _lib.ptr(buf["cA"]), _lib.ptr(buf["cB"]), st()))
+                                         float(lo), float(ub), _lib.ptr(cache["rhat"]), _lib.ptr(zcur), _lib.ptr(zprev),
+                                         _lib.ptr(cache["cA"]), _lib.ptr(cache["cB"]), int(split), st()))
         cshift = 0.5 * (ub + lo)
         for k in range(1, degree):
             # z_{k+1} overwrites z_{k-1}
-            _lib.check(h.scb_dense_slab_tf32_apply(self.N, 0, self.N, _lib.ptr(slab32), b, _lib.ptr(zcur),
-                                                   _lib.ptr(zprev), _lib.ptr(buf["rhat"]), _lib.ptr(zprev),
-                                                   _lib.ptr(buf["cA"][k]), _lib.ptr(buf["cB"][k]), cshift, 1, st()))
+            _lib.check(h.scb_dense_slab_tf32_apply(self.N, 0, self.N, _lib.ptr(hi), _lib.ptr(lo_slab), b,
+                                                   _lib.ptr(zcur), _lib.ptr(zprev), _lib.ptr(cache["rhat"]),
+                                                   _lib.ptr(zprev), _lib.ptr(cache["cA"][k]), _lib.ptr(cache["cB"][k]),
+                                                   cshift, 1, st()))
             zprev, zcur = zcur, zprev
-        _lib.check(h.scb_resform_finish(self.N, b, _lib.ptr(rn2), _lib.ptr(zcur), _lib.ptr(A), st()))
-        del znext
+        _lib.check(h.scb_resform_finish(self.N, b, _lib.ptr(rn2), _lib.ptr(zcur), _lib.ptr(A), int(split), st()))
         return A
 
     def close(self):
@@ -263,7 +271,7 @@ class DenseRowOperator:
         return Z[0]
 
 
-def lanczos_bound(op, start, steps=8, factor=1.03):
+def lanczos_bound(op, start, steps=12, factor=1.05):
     """Estimate of the largest eigenvalue from `steps` steps of column-wise Lanczos on the (random) block `start`
     (every column an independent run), times a safety factor: the Gershgorin bound of an all-pairs Hessian is
     ~3x too large, which costs ~1.7x more filter steps.  Collective when the operator is partitioned."""
@@ -298,27 +306,28 @@ def lanczos_bound(op, start, steps=8, factor=1.03):
     return float(out.item())
 
 
-def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200, lanczos_steps=8,
+def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, seed=0x5CB200, lanczos_steps=12,
                      filter=None):
     """The k lowest modes of the operator deflated by Z ([N][nz], orthonormal): returns
     (theta[b], X[N][b], resid[b], outer_iterations).  Columns 0..k-1 are converged to
     ``||H x - theta x|| <= tol * theta_k``.
 
     ``filter``: "fp64" = Chebyshev filter of the block itself with the FP64 slab kernel; "tf32" = residual-form
-    filter (the correction of every Ritz pair) on the TF32 tensor cores, FP64 everywhere else -- one GPU, 128-column
-    blocks (default there; ``SCB_DENSE_FILTER`` overrides)."""
+    filter (the correction of every Ritz pair) on the TF32 tensor cores as a 3-term split product (FP32-class
+    accuracy), "tf32x1" = the same with a single TF32 product (enough for small systems); FP64 everywhere else --
+    one GPU, 128-column blocks (default "tf32" there; ``SCB_DENSE_FILTER`` overrides)."""
     torch = _torch()
     h = op.handle
     st = _lib.stream_ptr
     N = op.N
     filter = filter or os.environ.get("SCB_DENSE_FILTER") or ("tf32" if op.world == 1 else "fp64")
-    if filter not in ("fp64", "tf32"):
-        raise ValueError("filter must be 'fp64' or 'tf32'")
+    if filter not in ("fp64", "tf32", "tf32x1"):
+        raise ValueError("filter must be 'fp64', 'tf32' or 'tf32x1'")
     if b is None:
-        b = 128 if (filter == "tf32" or k + 8 > 64) else 64
+        b = 128 if (filter != "fp64" or k + 8 > 64) else 64
     if k > b or b not in (64, 128):
         raise NotImplementedError(f"k={k} needs a block wider than 128 columns")
-    if filter == "tf32" and (op.world != 1 or b != 128):
+    if filter != "fp64" and (op.world != 1 or b != 128):
         filter = "fp64"
     nz = 0 if Z is None else int(Z.shape[1])
     if N < b + nz:
@@ -334,6 +343,7 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
     ub = min(ub_safe, lanczos_bound(op, A, steps=lanczos_steps)) if lanczos_steps else ub_safe
     theta = None
     lo = a0 = 0.0
+    lo_seen = None
     cur = A
 
     def orthonormalise(src, dst, also=None):
@@ -342,8 +352,9 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
         _lib.check(h.scb_rotate(1, N, b, _lib.ptr(Cm), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(also), _lib.ptr(also), st()))
 
     for outer in range(max_outer + 1):
-        if outer > 0 and filter == "tf32":
-            op.filter_residual_tf32(A, HX, theta, rn2, lo, ub, degree)   # A <- A + correction (nearly orthonormal)
+        if outer > 0 and filter != "fp64":
+            # A <- A + correction (nearly orthonormal)
+            op.filter_residual_tf32(A, HX, theta, rn2, lo, ub, degree, split=(filter == "tf32"))
             cur = A
         elif outer > 0:
             half, c = 0.5 * (ub - lo), 0.5 * (ub + lo)
@@ -358,7 +369,7 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
             cur = curb
         if nz:
             _lib.check(h.scb_deflate(1, N, b, nz, _lib.ptr(Z), _lib.ptr(cur), _lib.ptr(scratch), st()))
-        if not (outer > 0 and filter == "tf32"):
+        if not (outer > 0 and filter != "fp64"):
             orthonormalise(cur, A)      # the residual-form update keeps A well conditioned: CholQR below suffices
         HX = op.apply(A)
         orthonormalise(A, A, also=HX)          # second pass (CholQR2); H (A C) = (H A) C
@@ -378,10 +389,20 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
         th = theta.cpu().numpy()
         res = np.sqrt(np.maximum(rn2.cpu().numpy(), 0.0))
         a0 = float(th[0])
+        if os.environ.get("SCB_DENSE_TRACE"):
+            print(f"[dense] outer {outer} filter {filter} theta0 {th[0]:.4g} theta_k {th[k - 1]:.4g} theta_b {th[b - 1]:.4g} "
+                  f"ub {ub:.4g} res_max {res[:k].max():.3e}", flush=True)
         if outer > 0 and ub < ub_safe and th[b - 1] > 0.5 * ub:
             # a filtered block must sit far below the bound: the Lanczos estimate was too small, repair it
             ub = min(ub_safe, 1.15 * max(ub, float(th[b - 1])))
-        lo = min(float(th[b - 1]), 0.98 * ub)
+        # Lower edge of the damped interval = largest Ritz value of the block.  Once the block has been filtered the
+        # legitimate value only decreases; a jump upwards is a component from the top of the spectrum that leaked in
+        # (bound estimate slightly too small, single-precision noise) and must not drag the interval up with it.
+        top = float(th[b - 1])
+        lo = top if outer < 1 or lo_seen is None else min(top, lo_seen)
+        if outer >= 1:
+            lo_seen = lo
+        lo = min(lo, 0.98 * ub)
         if not lo > a0:
             lo = a0 + 0.5 * (ub - a0)
         if res[:k].max() <= tol * max(abs(th[k - 1]), 1e-6 * ub):

@@ -49,14 +49,17 @@ def test_c3_full_batch_properties():
     del torch, _lib
 
 
-def test_c4_full_size_properties():
-    """60,000 x 60,000 dense Hessian on one GPU (28.8 GB): residuals, orthonormality, null space."""
+@pytest.mark.parametrize("filt", ["tf32", "fp64"])
+def test_c4_full_size_properties(filt):
+    """60,000 x 60,000 dense Hessian on one GPU (28.8 GB): residuals, orthonormality, null space -- with the
+    residual-form filter on the TF32 tensor cores (3-term split product, + 28.8 GB of single-precision slabs) and
+    with the FP64 filter."""
     import torch
     from springcraft_b200 import _lib
     from springcraft_b200.dense_solver import DenseRowOperator, eig_lowest_dense
     free, _ = torch.cuda.mem_get_info()
-    if free < 60e9:
-        pytest.skip("needs ~45 GB of free device memory")
+    if free < 80e9:
+        pytest.skip("needs ~75 GB of free device memory")
     n, k = 20000, 100
     rng = np.random.default_rng(0)
     side = (n / 0.008) ** (1 / 3)
@@ -65,7 +68,7 @@ def test_c4_full_size_properties():
     coord = pts + rng.uniform(-0.25, 0.25, pts.shape) * (side / g) * 0.5      # min distance > 3 A
     op = DenseRowOperator(coord, sc.ParameterFreeForceField(), 3)
     Z = op.rigid_basis()
-    theta, X, resid, iters = eig_lowest_dense(op, k, Z=Z)
+    theta, X, resid, iters = eig_lowest_dense(op, k, Z=Z, filter=filt)
     th = theta.cpu().numpy()
     assert np.all(th[:k] > 0) and np.all(np.diff(th[:k]) >= 0)
     assert float(resid[:k].max()) <= 3e-9 * th[k - 1]

@@ -754,3 +754,60 @@ def test_tabulated_interaction_matrix_edited_in_place(structures):
         # the pristine force field gives a different matrix: the edit really went through the dense table
         H0, _ = sc.compute_hessian(atoms.coord, FF[key](atoms))
         assert not np.array_equal(H0, H)
+
+
+def test_dense_tf32_filter_kernel():
+    """tcgen05 TF32 slab product (dense_tf32.cu) against FP64 matmul: single product ~1e-3 (TF32), 3-term split
+    product at FP32 level; fused recurrence epilogue; ragged sizes (rows and K not multiples of the tile)."""
+    import torch
+    from springcraft_b200 import _lib
+    from springcraft_b200.dense_solver import DenseRowOperator
+    from synthetic_inputs import synthetic_cloud
+    h = _lib.require_device()
+    n, b = 250, 128
+    op = DenseRowOperator(synthetic_cloud(n, seed=2), sc.ParameterFreeForceField(), 3)
+    N = op.N
+    ld = int(h.scb_tf32_ld(N))
+    gen = torch.Generator("cuda").manual_seed(3)
+    Z = torch.zeros((b, ld), dtype=torch.float32, device="cuda")
+    Z[:, :N] = torch.randn((b, N), generator=gen, device="cuda")
+    ref = (op.slab @ Z[:, :N].double().T).T
+    scale = ref.abs().max().item()
+    s32, _ = op.slab32(False)
+    out = torch.full((b, ld), 7.0, dtype=torch.float32, device="cuda")
+    _lib.check(h.scb_dense_slab_tf32_apply(N, 0, N, _lib.ptr(s32), None, b, _lib.ptr(Z), None, None, _lib.ptr(out),
+                                           None, None, 0.0, 0, _lib.stream_ptr()))
+    assert (out[:, :N].double() - ref).abs().max().item() < 5e-3 * scale
+    assert bool((out[:, N:] == 7.0).all())                       # padding columns are never written
+    hi, lo = op.slab32(True)
+    assert torch.equal(hi.double()[:, :N] + lo.double()[:, :N], (hi.double() + lo.double())[:, :N])
+    assert (hi.double()[:, :N] + lo.double()[:, :N] - op.slab).abs().max().item() < 1e-9 * op.slab.abs().max().item()
+    Z2 = torch.zeros((2 * b, ld), dtype=torch.float32, device="cuda")
+    zh = (Z.view(torch.int32) & -8192).view(torch.float32)
+    Z2[:b], Z2[b:] = zh, Z - zh
+    Zp = torch.randn((2 * b, ld), generator=gen, device="cuda")
+    Rh = torch.randn((b, ld), generator=gen, device="cuda")
+    cA = torch.rand(b, generator=gen, device="cuda") * 0.1
+    cB = torch.rand(b, generator=gen, device="cuda")
+    zp = Zp[:b, :N].double() + Zp[b:, :N].double()
+    want = cA[:, None].double() * (ref - 0.7 * Z[:, :N].double() + Rh[:, :N].double()) - cB[:, None].double() * zp
+    _lib.check(h.scb_dense_slab_tf32_apply(N, 0, N, _lib.ptr(hi), _lib.ptr(lo), b, _lib.ptr(Z2), _lib.ptr(Zp),
+                                           _lib.ptr(Rh), _lib.ptr(Zp), _lib.ptr(cA), _lib.ptr(cB), 0.7, 1,
+                                           _lib.stream_ptr()))
+    got = Zp[:b, :N].double() + Zp[b:, :N].double()
+    assert (got - want).abs().max().item() < 5e-5 * want.abs().max().item()
+    op.close()
+
+
+@pytest.mark.parametrize("filt", ["tf32", "tf32x1", "fp64"])
+def test_c4_cloud400_filters(filt):
+    """C4 scaled down (reference golden): all-pairs pfENM, lowest 50 non-trivial modes with every filter variant."""
+    from springcraft_b200.dense_solver import DenseRowOperator, eig_lowest_dense
+    g = golden("ref_c4_cloud400.npz")
+    op = DenseRowOperator(g["coord"], sc.ParameterFreeForceField(), 3)
+    theta, X, res, it = eig_lowest_dense(op, 50, Z=op.rigid_basis(), b=128, filter=filt)
+    assert np.allclose(theta[:50].cpu().numpy(), g["eigval"][6:56], rtol=1e-8, atol=0)
+    Q, _ = np.linalg.qr(X[:, :50].cpu().numpy())
+    Qa, _ = np.linalg.qr(g["modes_6_106"][:50].T)
+    assert np.linalg.norm(Q - Qa @ (Qa.T @ Q), 2) < 1e-6
+    op.close()
