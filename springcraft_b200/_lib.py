@@ -203,4 +203,6 @@ def to_device(array, dtype):
     """NumPy -> contiguous device tensor of the given torch dtype."""
     import torch
     a = np.ascontiguousarray(array)
+    if not a.flags.writeable:        # e.g. arrays out of np.load: torch wants a writable source buffer
+        a = a.copy()
     return torch.from_numpy(a).to(device="cuda", dtype=dtype)
