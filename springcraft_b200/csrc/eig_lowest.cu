@@ -210,7 +210,7 @@ extern "C" int scb_eig_lowest(int D, int B, int n, int64_t P, const int64_t* row
             if (*h_active == 0 || outer == max_outer) break;
             if (prof) cudaEventRecord(ev0, st);
             if ((status = resident_filter(B, n, b, rowptr, w.res, w.A, w.HX, w.theta, w.rn2, w.state, done, Z, nz,
-                                          w.A, st)) != SCB_OK)
+                                          w.A, k, tol, st)) != SCB_OK)
                 break;
             if (prof) {   // scb_profile: device time of the filter launches (the stream is synchronised once per
                           // outer iteration anyway; the extra synchronisation only exists while profiling)

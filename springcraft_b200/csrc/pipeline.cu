@@ -186,7 +186,9 @@ extern "C" int scb_enm_ensemble(int D, const double* xyz, int B, int n, const sc
         return hflag != 0 ? hflag : SCB_OK;
     }
     SCB_TRY(scb_rigid_basis(D, xyz, B, n, masses, Z, st));
-    int degree = 32;   // measured optimum on the C3 batch with the adaptive last iterations (24: -4 %, 40: -4 %)
+    // filter degree: measured on the C3 batch with the structure-resident FP32 filter (step time): 24: 256 ms,
+    // 28: 250, 32: 247, 36: 247, 40: 240, 48: 275
+    int degree = 40;
     if (const char* env = getenv("SCB_DEGREE")) degree = atoi(env) >= 2 ? atoi(env) : degree;
     int status = scb_eig_lowest(D, B, n, P, rowptr, col, offdiag, diag, gersh, Z, nz, k, b, tol, 200, degree,
                                 0x5cb200ull, theta, X, resid, it, ws, ws_bytes, st);

@@ -54,7 +54,8 @@ int resident_build(int B, int n, const int64_t* rowptr, const int32_t* col, cons
 // X <- deflate(X + |r| z) for every active structure: one CTA per (structure, column group)
 int resident_filter(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, const double* X,
                     const double* HX, const double* theta, const double* rn2, const EigState* state,
-                    const int32_t* done, const double* Z, int nz, double* Xout, cudaStream_t st);
+                    const int32_t* done, const double* Z, int nz, double* Xout, int kwant, double tol,
+                    cudaStream_t st);
 // upper spectrum bound from `steps` steps of column-wise Lanczos (FP32, structure-resident): state[s].ub
 int resident_lanczos(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, int steps, uint64_t seed,
                      double ub_factor, EigState* state, cudaStream_t st);

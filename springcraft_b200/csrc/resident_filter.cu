@@ -162,7 +162,7 @@ resident_filter_kernel(int n, int b, int G, int rec_mul, int64_t rec_pad, const 
                        const double* X, const double* __restrict__ HX, const double* __restrict__ theta,
                        const double* __restrict__ rn2, const EigState* __restrict__ state,
                        const int32_t* __restrict__ done, const double* __restrict__ Zr, int nz, double* Xout,
-                       unsigned long long* __restrict__ app_counter) {
+                       unsigned long long* __restrict__ app_counter, int kwant, double tol) {
     constexpr int LPP = COLS / 4;        // lanes per row pair
     constexpr int RPW = 32 / LPP;        // row pairs per warp (group size)
     extern __shared__ __align__(16) float res_smem[];
@@ -185,6 +185,16 @@ resident_filter_kernel(int n, int b, int G, int rec_mul, int64_t rec_pad, const 
     const EigState e = state[s];
     int deg = e.degree_next;
     deg = deg < 2 ? 2 : (deg > kResDegreeCap ? kResDegreeCap : deg);
+    // A column group whose columns are all WANTED modes that already meet the tolerance (with a margin) needs no
+    // further correction: the lowest modes converge first, so in the last outer iterations the CTA of columns 0..15
+    // retires while the group holding the highest wanted modes and the guard vectors keeps filtering.
+    if ((cg + 1) * COLS <= kwant) {
+        const double scale = fmax(fabs(theta[s * b + kwant - 1]), 1e-6 * e.ub);
+        const double lim = 0.1 * tol * scale;
+        bool all_done = true;
+        for (int c = 0; c < COLS; ++c) all_done = all_done && (rn2[s * b + cg * COLS + c] <= lim * lim);
+        if (all_done) return;
+    }
     // bench accounting: operator applications per structure (integer adds commute: the total is reproducible)
     if (app_counter && tid == 0 && cg == 0) atomicAdd(app_counter, (unsigned long long)(deg - 1));
     const double ehalf = 0.5 * (e.ub - e.lo), cmid = 0.5 * (e.ub + e.lo);
@@ -586,7 +596,8 @@ static size_t filter_smem(int n, int cols) {
 template <int COLS>
 static int launch_filter(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, const double* X,
                          const double* HX, const double* theta, const double* rn2, const EigState* state,
-                         const int32_t* done, const double* Z, int nz, double* Xout, cudaStream_t st) {
+                         const int32_t* done, const double* Z, int nz, double* Xout, int kwant, double tol,
+                         cudaStream_t st) {
     const size_t smem = filter_smem(n, COLS);
     // groups per warp: 2 pairs the k-th longest with the k-th shortest group (balanced warps, half the threads);
     // measured on the C3 batch: 1 group per warp (20 warps) 310 ms per step, 2 groups (10 warps) 317 ms
@@ -599,12 +610,12 @@ static int launch_filter(int B, int n, int b, const int64_t* rowptr, const ResLa
         SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resident_filter_kernel<COLS, 1><<<grid, 32 * 4 * ((L.G + 3) / 4), smem, st>>>(
             n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz,
-            Xout, L.app_counter);
+            Xout, L.app_counter, kwant, tol);
     } else {
         SCB_CUDA(cudaFuncSetAttribute(resident_filter_kernel<COLS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         resident_filter_kernel<COLS, 2><<<grid, 32 * ((L.G + 1) / 2), smem, st>>>(
             n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec, L.gstart, L.order, L.diag32, X, HX, theta, rn2, state, done, Z, nz,
-            Xout, L.app_counter);
+            Xout, L.app_counter, kwant, tol);
     }
     SCB_LAUNCH_CHECK();
     return SCB_OK;
@@ -639,11 +650,12 @@ int resident_lanczos(int B, int n, int b, const int64_t* rowptr, const ResLayout
 
 int resident_filter(int B, int n, int b, const int64_t* rowptr, const ResLayout& L, const double* X,
                     const double* HX, const double* theta, const double* rn2, const EigState* state,
-                    const int32_t* done, const double* Z, int nz, double* Xout, cudaStream_t st) {
+                    const int32_t* done, const double* Z, int nz, double* Xout, int kwant, double tol,
+                    cudaStream_t st) {
     if (nz > 8) return SCB_ERR_UNSUPPORTED;
-    if (L.cols == 16) return launch_filter<16>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, st);
-    if (L.cols == 8) return launch_filter<8>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, st);
-    if (L.cols == 4) return launch_filter<4>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, st);
+    if (L.cols == 16) return launch_filter<16>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, kwant, tol, st);
+    if (L.cols == 8) return launch_filter<8>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, kwant, tol, st);
+    if (L.cols == 4) return launch_filter<4>(B, n, b, rowptr, L, X, HX, theta, rn2, state, done, Z, nz, Xout, kwant, tol, st);
     return SCB_ERR_UNSUPPORTED;
 }
 
