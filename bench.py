@@ -500,7 +500,7 @@ def run_gpu(args):
             op.apply(X4)
             ms_app = timed(lambda: op.apply(X4), 3)[0] / 3
             Z4 = op.rigid_basis()
-            filt = "tf32" if world == 1 else "fp64"
+            filt = "tf32"
             if filt == "tf32":
                 op.slab32(True)                      # single-precision copies of the slab (part of the setup)
             barrier()
@@ -516,12 +516,12 @@ def run_gpu(args):
                 "fp64_slab_product": {"ms_per_application": ms_app, "tflops_aggregate": fl4 / (ms_app * 1e-3) / 1e12,
                                       "frac_of_dgemm": fl4 / (ms_app * 1e-3) / 1e12 / (dgemm * world),
                                       "use": "H X once per outer iteration" + ("" if filt == "tf32" else " and every filter step")},
-                "filter": ("residual form, 3-term TF32 split product on the 5th-generation tensor cores (tcgen05.mma "
-                           "kind::tf32, TMA operands, TMEM accumulator)") if filt == "tf32" else
-                          "FP64 slab product with the all-gather fused into its epilogue",
+                "filter": "residual form, 3-term TF32 split product on the 5th-generation tensor cores (tcgen05.mma "
+                          "kind::tf32, TMA operands, TMEM accumulator)" + ("" if world == 1 else
+                          "; every rank filters its row slab and stores the rows into the peer-mapped blocks of all ranks"),
                 "solve_seconds": t_solve, "outer_iterations": int(it4),
                 "max_residual_over_lambda_k": float((res4[:k4].max() / theta4[k4 - 1]).item())}
-            if filt == "tf32":
+            if world == 1:
                 hi32, lo32 = op.slab32(True)
                 ld4 = int(handle.scb_tf32_ld(3 * n4))
                 zc = torch.randn((2 * b4, ld4), dtype=torch.float32, device="cuda")

@@ -258,6 +258,14 @@ int scb_resform_prepare(int64_t N, int b, int deg, const double *X, const double
 int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float *slab32, const float *slab32_lo,
                               int b, const float *zcurT, const float *zprevT, const float *rhatT, float *outT,
                               const float *cA, const float *cB, double cshift, int fused, void *stream);
+/* The same step with the all-gather of the row slabs fused into the epilogue: out_all is a HOST array of `world`
+ * (<= 8) device pointers, out_all[p] = the output block of rank p mapped into this process (scb_peer_open; rank's own
+ * buffer first or anywhere); rows [row0,row1) are stored into every block over NVLink.  The caller runs a barrier
+ * collective before any rank reads its block.  zprevT is this rank's copy of the block that is being overwritten. */
+int scb_dense_slab_tf32_apply_allgather(int64_t N, int64_t row0, int64_t row1, const float *slab32,
+                                        const float *slab32_lo, int b, const float *zcurT, const float *zprevT,
+                                        const float *rhatT, float *const *out_all, int world, const float *cA,
+                                        const float *cB, double cshift, int fused, void *stream);
 int scb_resform_finish(int64_t N, int b, const double *rn2, const float *zT, double *X, int split, void *stream);
 /* Column-wise Lanczos (every column of a block is an independent Lanczos run; spectrum bound of an operator the
  * caller applies, e.g. the dense row-slab operator).  b = 32, 64 or 128.

@@ -105,6 +105,7 @@ SIGNATURES = {
     "scb_dense_slab_to_f32": (_I, [_I64, _I64, _P, _P, _P, _P]),
     "scb_resform_prepare": (_I, [_I64, _I, _I, _P, _P, _P, _P, _D, _D, _P, _P, _P, _P, _P, _I, _P]),
     "scb_dense_slab_tf32_apply": (_I, [_I64, _I64, _I64, _P, _P, _I, _P, _P, _P, _P, _P, _P, _D, _I, _P]),
+    "scb_dense_slab_tf32_apply_allgather": (_I, [_I64, _I64, _I64, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _I, _P]),
     "scb_resform_finish": (_I, [_I64, _I, _P, _P, _P, _I, _P]),
     "scb_coldot": (_I, [_I, _I64, _I, _P, _P, _P, _P]),
     "scb_lanczos_axpy": (_I, [_I, _I64, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -107,7 +107,8 @@ struct T32Epilogue {
     const float* zcur;     // [b][ld]  Zcur^T   (NULL: plain product, out = H Z)
     const float* zprev;    // [b][ld]  Zprev^T
     const float* rhat;     // [b][ld]  normalised residual, transposed
-    float* out;            // [b][ld]  Znext^T (may alias zprev)
+    float* out[8];         // [b][ld]  Znext^T (may alias zprev) in the buffers of every rank (peer mapped); out[0] = own
+    int nout;              // number of destinations (1 on one GPU)
     const float* cA;       // [b]
     const float* cB;       // [b]
     float cshift;
@@ -218,12 +219,16 @@ dense_slab_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     if (SPLIT == 3) { zc += ep.zcur[idx + lo_off]; zp += ep.zprev[idx + lo_off]; }
                     v = ep.cA[n] * (fmaf(-ep.cshift, zc, v) + ep.rhat[idx]) - ep.cB[n] * zp;
                 }
+                // the all-gather of the row slabs is fused here: the result goes straight into the block of every rank
                 if (SPLIT == 3) {
                     const float hi = tf32_hi(v);
-                    ep.out[idx] = hi;
-                    ep.out[idx + lo_off] = v - hi;
+                    const float lo = v - hi;
+                    for (int p = 0; p < ep.nout; ++p) {
+                        ep.out[p][idx] = hi;
+                        ep.out[p][idx + lo_off] = lo;
+                    }
                 } else {
-                    ep.out[idx] = v;
+                    for (int p = 0; p < ep.nout; ++p) ep.out[p][idx] = v;
                 }
             }
         }
@@ -409,11 +414,11 @@ extern "C" int scb_resform_finish(int64_t N, int b, const double* rn2, const flo
     return SCB_OK;
 }
 
-extern "C" int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float* slab32,
-                                         const float* slab32_lo, int b, const float* zcurT, const float* zprevT,
-                                         const float* rhatT, float* outT, const float* cA, const float* cB,
-                                         double cshift, int fused, void* stream) {
-    if (!slab32 || !zcurT || !outT || N < 1 || row0 < 0 || row1 <= row0 || row1 > N) return SCB_ERR_INVALID;
+static int tf32_apply(int64_t N, int64_t row0, int64_t row1, const float* slab32, const float* slab32_lo, int b,
+                      const float* zcurT, const float* zprevT, const float* rhatT, float* const* outs, int nout,
+                      const float* cA, const float* cB, double cshift, int fused, cudaStream_t st) {
+    if (!slab32 || !zcurT || !outs || nout < 1 || nout > 8 || N < 1 || row0 < 0 || row1 <= row0 || row1 > N)
+        return SCB_ERR_INVALID;
     if (b != kT32BN) return SCB_ERR_UNSUPPORTED;
     if (fused && (!zprevT || !rhatT || !cA || !cB)) return SCB_ERR_INVALID;
     const int64_t ld = scb_tf32_ld(N);
@@ -425,10 +430,11 @@ extern "C" int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, 
     SCB_TRY(make_map(&mapAlo, split ? slab32_lo : slab32, N, rows, ld, kT32BM));
     SCB_TRY(make_map(&mapBlo, split ? zcurT + (int64_t)b * ld : zcurT, N, b, ld, kT32BN));
     T32Epilogue ep;
-    ep.zcur = fused ? zcurT : nullptr; ep.zprev = zprevT; ep.rhat = rhatT; ep.out = outT;
+    ep.zcur = fused ? zcurT : nullptr; ep.zprev = zprevT; ep.rhat = rhatT;
+    for (int p = 0; p < 8; ++p) ep.out[p] = p < nout ? outs[p] : nullptr;
+    ep.nout = nout;
     ep.cA = cA; ep.cB = cB; ep.cshift = (float)cshift; ep.ld = ld; ep.row0 = (int)row0; ep.rows = (int)rows;
     const unsigned grid = (unsigned)ceil_div(rows, kT32BM);
-    cudaStream_t st = as_stream(stream);
     if (split) {
         const size_t smem = (size_t)kT32Stages * 4 * kT32TileBytes + 1024;
         SCB_CUDA(cudaFuncSetAttribute(dense_slab_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -440,4 +446,23 @@ extern "C" int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, 
     }
     SCB_LAUNCH_CHECK();
     return SCB_OK;
+}
+
+extern "C" int scb_dense_slab_tf32_apply(int64_t N, int64_t row0, int64_t row1, const float* slab32,
+                                         const float* slab32_lo, int b, const float* zcurT, const float* zprevT,
+                                         const float* rhatT, float* outT, const float* cA, const float* cB,
+                                         double cshift, int fused, void* stream) {
+    if (!outT) return SCB_ERR_INVALID;
+    float* outs[1] = {outT};
+    return tf32_apply(N, row0, row1, slab32, slab32_lo, b, zcurT, zprevT, rhatT, outs, 1, cA, cB, cshift, fused,
+                      as_stream(stream));
+}
+
+extern "C" int scb_dense_slab_tf32_apply_allgather(int64_t N, int64_t row0, int64_t row1, const float* slab32,
+                                                   const float* slab32_lo, int b, const float* zcurT,
+                                                   const float* zprevT, const float* rhatT, float* const* out_all,
+                                                   int world, const float* cA, const float* cB, double cshift,
+                                                   int fused, void* stream) {
+    return tf32_apply(N, row0, row1, slab32, slab32_lo, b, zcurT, zprevT, rhatT, out_all, world, cA, cB, cshift, fused,
+                      as_stream(stream));
 }

@@ -34,8 +34,8 @@ def _torch():
 class _RawBlock:
     """CUDA array interface over a raw device pointer (lets torch view a peer-mapped buffer)."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 3, "strides": None}
 
 
@@ -47,13 +47,15 @@ class PeerBlockPool:
     host array of `world` device pointers that `scb_dense_slab_apply_allgather` takes for block i.
     Collective: construct, use and close it from every rank in the same order."""
 
-    def __init__(self, N, b, count=4):
+    def __init__(self, N, b, count=4, typestr="<f8"):
+        """``typestr`` "<f8": [N][b] fp64 blocks (FP64 slab product); "<f4": [N][b] float32 (the transposed
+        [2 b][ld] blocks of the TF32 filter are requested as N = 2 b rows of b = ld columns)."""
         torch = _torch()
         import torch.distributed as dist
         self.handle = _lib.require_device()
         self.rank, self.world = world()
         self.N, self.b, self.count = int(N), int(b), int(count)
-        nbytes = self.N * self.b * 8
+        nbytes = self.N * self.b * int(typestr[2:])
         self._local, self._opened = [], []
         handles = torch.empty((self.count, 64), dtype=torch.uint8)
         for i in range(self.count):
@@ -79,7 +81,7 @@ class PeerBlockPool:
                 self._opened.append(out.value)
                 ptrs.append(out.value)
             self._tables.append((C.c_void_p * self.world)(*ptrs))
-            self.blocks.append(torch.as_tensor(_RawBlock(self._local[i], (self.N, self.b)), device="cuda"))
+            self.blocks.append(torch.as_tensor(_RawBlock(self._local[i], (self.N, self.b), typestr), device="cuda"))
         self._token = torch.zeros(1, dtype=torch.float32, device="cuda")
         self._next = 0
         self._dist = dist
@@ -216,37 +218,60 @@ class DenseRowOperator:
         torch = _torch()
         h, st = self.handle, _lib.stream_ptr
         b = int(A.shape[1])
-        if self.world != 1 or b != 128:
-            raise NotImplementedError("the TF32 filter runs on one GPU with 128-column blocks")
+        if b != 128:
+            raise NotImplementedError("the TF32 filter needs 128-column blocks")
         ld = int(h.scb_tf32_ld(self.N))
         rows = 2 * b if split else b
         cache = getattr(self, "_tf32_buffers", None)
         if cache is None or cache["rows"] != rows:
+            if self.world > 1:
+                # the z blocks live in peer-mapped memory: every rank stores its rows into the blocks of all ranks
+                pool = self._pools[("tf32", rows)] = PeerBlockPool(rows, ld, count=2, typestr="<f4")
+                z = pool.blocks
+            else:
+                pool = None
+                z = [torch.empty((rows, ld), dtype=torch.float32, device="cuda") for _ in range(2)]
             cache = self._tf32_buffers = {
-                "rows": rows,
-                "z": [torch.empty((rows, ld), dtype=torch.float32, device="cuda") for _ in range(2)],
+                "rows": rows, "pool": pool, "z": z,
                 "rhat": torch.empty((b, ld), dtype=torch.float32, device="cuda"),
                 "cA": torch.empty((64, b), dtype=torch.float32, device="cuda"),
                 "cB": torch.empty((64, b), dtype=torch.float32, device="cuda")}
         degree = int(min(max(degree, 2), 64))
-        zprev, zcur = cache["z"]
+        pool = cache["pool"]
+        iprev, icur = 0, 1
+        z = cache["z"]
         hi, lo_slab = self.slab32(split)
+        if pool is not None:
+            pool.barrier()       # nobody still reads the blocks of the previous filter
+        # replicated: every rank prepares the complete blocks from its copies of A, HX, theta, rn2
         _lib.check(h.scb_resform_prepare(self.N, b, degree, _lib.ptr(A), _lib.ptr(HX), _lib.ptr(theta), _lib.ptr(rn2),
-                                         float(lo), float(ub), _lib.ptr(cache["rhat"]), _lib.ptr(zcur), _lib.ptr(zprev),
-                                         _lib.ptr(cache["cA"]), _lib.ptr(cache["cB"]), int(split), st()))
+                                         float(lo), float(ub), _lib.ptr(cache["rhat"]), _lib.ptr(z[icur]),
+                                         _lib.ptr(z[iprev]), _lib.ptr(cache["cA"]), _lib.ptr(cache["cB"]), int(split),
+                                         st()))
+        if pool is not None:
+            pool.barrier()       # every rank has initialised its blocks before remote rows arrive
         cshift = 0.5 * (ub + lo)
+        r0, r1 = self.row0 * self.D, self.row1 * self.D
         for k in range(1, degree):
-            # z_{k+1} overwrites z_{k-1}
-            _lib.check(h.scb_dense_slab_tf32_apply(self.N, 0, self.N, _lib.ptr(hi), _lib.ptr(lo_slab), b,
-                                                   _lib.ptr(zcur), _lib.ptr(zprev), _lib.ptr(cache["rhat"]),
-                                                   _lib.ptr(zprev), _lib.ptr(cache["cA"][k]), _lib.ptr(cache["cB"][k]),
-                                                   cshift, 1, st()))
-            zprev, zcur = zcur, zprev
-        _lib.check(h.scb_resform_finish(self.N, b, _lib.ptr(rn2), _lib.ptr(zcur), _lib.ptr(A), int(split), st()))
+            # z_{k+1} overwrites z_{k-1}; rows [r0, r1) of the result go into the block of every rank
+            if pool is None:
+                _lib.check(h.scb_dense_slab_tf32_apply(self.N, r0, r1, _lib.ptr(hi), _lib.ptr(lo_slab), b,
+                                                       _lib.ptr(z[icur]), _lib.ptr(z[iprev]), _lib.ptr(cache["rhat"]),
+                                                       _lib.ptr(z[iprev]), _lib.ptr(cache["cA"][k]),
+                                                       _lib.ptr(cache["cB"][k]), cshift, 1, st()))
+            else:
+                _lib.check(h.scb_dense_slab_tf32_apply_allgather(
+                    self.N, r0, r1, _lib.ptr(hi), _lib.ptr(lo_slab), b, _lib.ptr(z[icur]), _lib.ptr(z[iprev]),
+                    _lib.ptr(cache["rhat"]), pool.table(iprev), self.world, _lib.ptr(cache["cA"][k]),
+                    _lib.ptr(cache["cB"][k]), cshift, 1, st()))
+                pool.barrier()
+            iprev, icur = icur, iprev
+        _lib.check(h.scb_resform_finish(self.N, b, _lib.ptr(rn2), _lib.ptr(z[icur]), _lib.ptr(A), int(split), st()))
         return A
 
     def close(self):
         """Release the peer-mapped blocks (collective; tensors returned by `apply` die with them)."""
+        self._tf32_buffers = None
         for pool in self._pools.values():
             pool.close()
         self._pools = {}
@@ -316,19 +341,20 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
     ``filter``: "fp64" = Chebyshev filter of the block itself with the FP64 slab kernel; "tf32" = residual-form
     filter (the correction of every Ritz pair) on the TF32 tensor cores as a 3-term split product (FP32-class
     accuracy), "tf32x1" = the same with a single TF32 product (enough for small systems); FP64 everywhere else --
-    one GPU, 128-column blocks (default "tf32" there; ``SCB_DENSE_FILTER`` overrides)."""
+    128-column blocks (default "tf32"; ``SCB_DENSE_FILTER`` overrides).  On several GPUs every rank filters its
+    row slab and stores the result into the peer-mapped blocks of all ranks (fused all-gather)."""
     torch = _torch()
     h = op.handle
     st = _lib.stream_ptr
     N = op.N
-    filter = filter or os.environ.get("SCB_DENSE_FILTER") or ("tf32" if op.world == 1 else "fp64")
+    filter = filter or os.environ.get("SCB_DENSE_FILTER") or "tf32"
     if filter not in ("fp64", "tf32", "tf32x1"):
         raise ValueError("filter must be 'fp64', 'tf32' or 'tf32x1'")
     if b is None:
         b = 128 if (filter != "fp64" or k + 8 > 64) else 64
     if k > b or b not in (64, 128):
         raise NotImplementedError(f"k={k} needs a block wider than 128 columns")
-    if filter != "fp64" and (op.world != 1 or b != 128):
+    if filter != "fp64" and b != 128:
         filter = "fp64"
     nz = 0 if Z is None else int(Z.shape[1])
     if N < b + nz:
@@ -411,10 +437,10 @@ def eig_lowest_dense(op, k, Z=None, b=None, tol=3e-9, degree=24, max_outer=300, 
     raise RuntimeError(_lib.lib().scb_status_string(_lib.SCB_ERR_NOT_CONVERGED).decode())
 
 
-def allpairs_lowest_modes(coord, force_field, k, kind="anm", masses=None, tol=3e-9, exchange=None):
+def allpairs_lowest_modes(coord, force_field, k, kind="anm", masses=None, tol=3e-9, exchange=None, filter=None):
     """``eigen(k=...)`` for all-pairs force fields on the dense row-partitioned path: the k lowest
     modes INCLUDING the trivial ones (analytic rigid-body basis, eigenvalue 0), rows = modes.
-    Call it from every rank of the process group; the result is replicated."""
+    Call it from every rank of the process group; the result is replicated.  ``filter``: see eig_lowest_dense."""
     torch = _torch()
     D = 3 if kind == "anm" else 1
     ntriv = 6 if D == 3 else 1
@@ -422,7 +448,7 @@ def allpairs_lowest_modes(coord, force_field, k, kind="anm", masses=None, tol=3e
     Z = op.rigid_basis()
     kk = max(k - ntriv, 1)
     try:
-        theta, X, _, iters = eig_lowest_dense(op, kk, Z=Z, tol=tol)
+        theta, X, _, iters = eig_lowest_dense(op, kk, Z=Z, tol=tol, filter=filter)
         lam = torch.cat([torch.zeros(ntriv, dtype=torch.float64, device="cuda"), theta[:kk]])
         modes = torch.cat([Z.T.contiguous(), X[:, :kk].T.contiguous()])
         return lam[:k].cpu().numpy(), modes[:k].cpu().numpy(), iters

@@ -33,9 +33,14 @@ def run_checks():
     # a borderline tolerance: rounding differences between the ranks must not split the collective decisions
     lam4b, _, _ = sc.allpairs_lowest_modes(g["coord"], sc.ParameterFreeForceField(), 56, tol=1e-6)
     assert np.allclose(lam4b[6:56], g["eigval"][6:56], rtol=1e-6), "C4 loose tolerance"
-    # the same solve with the plain NCCL all-gather instead of the fused peer-memory epilogue
-    lam4n, _, it4n = sc.allpairs_lowest_modes(g["coord"], sc.ParameterFreeForceField(), 56, exchange="nccl")
-    assert it4n == it4 and np.allclose(lam4n, lam4, rtol=1e-11, atol=1e-12), "peer vs nccl exchange"
+    # the FP64 filter (slab product with the fused peer-memory all-gather) and the same solve with the plain NCCL
+    # all-gather instead of the fused epilogue
+    lam4f, _, it4f = sc.allpairs_lowest_modes(g["coord"], sc.ParameterFreeForceField(), 56, filter="fp64")
+    assert np.allclose(lam4f[6:56], g["eigval"][6:56], rtol=1e-8, atol=0), "C4 eigenvalues, FP64 filter"
+    lam4n, _, it4n = sc.allpairs_lowest_modes(g["coord"], sc.ParameterFreeForceField(), 56, exchange="nccl",
+                                              filter="fp64")
+    assert it4n == it4f and np.allclose(lam4n, lam4f, rtol=1e-11, atol=1e-12), "peer vs nccl exchange"
+    report["c4_cloud400"]["outer_iterations_fp64_filter"] = int(it4f)
     # one operator application, both exchanges, bit for bit
     gen = torch.Generator("cuda").manual_seed(7)
     Xb = torch.randn((3 * len(g["coord"]), 64), dtype=torch.float64, device="cuda", generator=gen)
