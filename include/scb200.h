@@ -315,6 +315,12 @@ int scb_covariance(int N, int m, const double *lam, const double *modes, int row
 int scb_linear_response(int N, int m, const double *lam, const double *modes,
                         const double *force, double *out, void *workspace,
                         size_t workspace_bytes, void *stream);
+/* Products of a covariance matrix ASSIGNED by the caller (anm.py:138-148: `enm.covariance = C`), which the reference
+ * then uses as is: dcc (nma.py:324-357: 3x3 traces for ANM, optional normalisation by sqrt(d_ii d_jj) BEFORE the
+ * temperature scale; diag_scratch[n] needed when norm != 0) and linear response y = C f (nma.py:473). */
+int scb_dcc_from_covariance(int D, int n, const double *cov, int norm, double scale, double *out,
+                            double *diag_scratch, void *stream);
+int scb_symv(int N, const double *cov, const double *f, double *y, void *stream);
 /* perturbation response scanning matrix (nma.py:511-531): out[n][n] from the covariance cov[3n][3n];
  * norm != 0 divides row i by out[i][i] */
 int scb_prs(int n, const double *cov, int norm, double *out, void *stream);

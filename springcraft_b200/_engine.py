@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["DeviceModel", "eig_full_dense", "modes_msf", "modes_dcc", "modes_covariance",
-           "modes_linear_response"]
+           "modes_linear_response", "cov_dcc", "cov_matvec"]
 
 # structures up to this size keep an explicit CSR for all-pairs force fields
 # (bit-exact diagonal); larger ones are assembled straight into dense slabs
@@ -318,3 +318,27 @@ def modes_linear_response(lam, modes, force):
     _lib.check(h.scb_linear_response(N, m, _lib.ptr(lam), _lib.ptr(modes), _lib.ptr(force), _lib.ptr(out),
                                      _lib.ptr(ws), 8 * m + 256, _lib.stream_ptr()))
     return out
+
+
+def cov_dcc(D, cov, norm=True, scale=1.0):
+    """DCC from a covariance matrix assigned by the caller (nma.py:324-357)."""
+    torch = _torch()
+    h = _lib.require_device()
+    c = torch.from_numpy(np.ascontiguousarray(cov, dtype=np.float64)).cuda()
+    n = int(c.shape[0]) // D
+    out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    diag = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(h.scb_dcc_from_covariance(D, n, _lib.ptr(c), int(bool(norm)), float(scale), _lib.ptr(out),
+                                         _lib.ptr(diag), _lib.stream_ptr()))
+    return out
+
+
+def cov_matvec(cov, force):
+    """cov @ force for a covariance assigned by the caller (nma.py:473)."""
+    torch = _torch()
+    h = _lib.require_device()
+    c = torch.from_numpy(np.ascontiguousarray(cov, dtype=np.float64)).cuda()
+    f = _lib.to_device(force, torch.float64)
+    y = torch.empty(int(c.shape[0]), dtype=torch.float64, device="cuda")
+    _lib.check(h.scb_symv(int(c.shape[0]), _lib.ptr(c), _lib.ptr(f), _lib.ptr(y), _lib.stream_ptr()))
+    return y

@@ -35,12 +35,32 @@ class ENMBase:
         self._matrix = None        # host dense Hessian / Kirchhoff
         self._covariance = None    # host dense covariance
         self._user_matrix = False  # matrix (or covariance) was assigned by the caller
+        self._user_covariance = False
+        self._exposed_token = None  # fingerprint of the host matrix at the time it was handed to the caller
         self._model = None
         self._spectrum_cache = {}
 
     # ---- device side ---------------------------------------------------------
     def _has_model(self):
+        self._sync_exposed()
         return not self._user_matrix
+
+    def _matrix_token(self):
+        M = self._matrix
+        return (float(M.sum()), float(np.vdot(M, M)), float(M.flat[:: max(1, M.size // 97)].sum()))
+
+    def _sync_exposed(self):
+        """`enm.hessian` / `enm.kirchhoff` return the cached array itself, not a copy (anm.py:53-57); the reference
+        therefore sees in-place edits by the caller at the next eigen()/MSF/... call.  The device model cannot, so
+        the array's fingerprint is compared with the one taken when it was handed out: if it changed, the host array
+        becomes the source of truth (dense path) and cached spectra are dropped."""
+        if self._matrix is None or self._exposed_token is None:
+            return
+        token = self._matrix_token()
+        if token != self._exposed_token:
+            self._exposed_token = token
+            self._user_matrix = True
+            self._spectrum_cache = {}
 
     def _model_device(self):
         if self._model is None:
@@ -72,6 +92,10 @@ class ENMBase:
                 self._matrix = self._model_device().dense()[0].cpu().numpy()
             else:
                 self._matrix = self._pinv_device(self._covariance)
+        if self._exposed_token is None:
+            self._exposed_token = self._matrix_token()
+        else:
+            self._sync_exposed()
         return self._matrix
 
     def _set_matrix(self, value, exc):
@@ -81,6 +105,8 @@ class ENMBase:
         self._matrix = value
         self._covariance = None
         self._user_matrix = True
+        self._user_covariance = False
+        self._exposed_token = self._matrix_token()
         self._spectrum_cache = {}
 
     @property
@@ -103,6 +129,8 @@ class ENMBase:
         self._covariance = value
         self._matrix = None
         self._user_matrix = True
+        self._user_covariance = True
+        self._exposed_token = None
         self._spectrum_cache = {}
 
     # ---- NMA methods shared by both models -----------------------------------

@@ -119,6 +119,8 @@ SIGNATURES = {
     "scb_dcc_workspace_bytes": (_SZ, [_I, _I, _I]),
     "scb_covariance": (_I, [_I, _I, _P, _P, _I, _I, _P, _P, _SZ, _P]),
     "scb_linear_response": (_I, [_I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "scb_dcc_from_covariance": (_I, [_I, _I, _P, _I, _D, _P, _P, _P]),
+    "scb_symv": (_I, [_I, _P, _P, _P, _P]),
     "scb_prs": (_I, [_I, _P, _I, _P, _P]),
     "scb_normal_mode": (_I, [_I, _I, _P, _D, _I, _P, _P]),
     "scb_export_modes": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),

@@ -408,6 +408,68 @@ extern "C" int scb_linear_response(int N, int m, const double* lam, const double
     return SCB_OK;
 }
 
+// ---- products of a covariance matrix that the CALLER assigned (anm.covariance = C, anm.py:138-148): the reference
+// then serves dcc() and linear_response() from that matrix (nma.py:324-336, 473), not from an eigendecomposition
+namespace scb {
+// out[i][j] = scale * sum_a C[D i + a][D j + a]  (nma.py:329-336); raw (un-normalised) values
+__global__ void __launch_bounds__(256)
+dcc_from_cov_kernel(int D, int n, const double* __restrict__ cov, double scale, double* __restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)n * n) return;
+    const int i = (int)(q / n), j = (int)(q % n);
+    const int64_t N = (int64_t)D * n;
+    double t = 0.0;
+    for (int a = 0; a < D; ++a) t += cov[((int64_t)D * i + a) * N + (int64_t)D * j + a];
+    out[q] = scale * t;
+}
+// out[i][j] /= sqrt(d_i d_j) with d = the diagonal BEFORE scaling by `scale` (normalisation first, nma.py:350-357)
+__global__ void __launch_bounds__(256)
+dcc_normalise_kernel(int n, const double* __restrict__ diag, double scale, double* __restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)n * n) return;
+    const int i = (int)(q / n), j = (int)(q % n);
+    out[q] = out[q] / sqrt((diag[i] / scale) * (diag[j] / scale));
+}
+__global__ void __launch_bounds__(256)
+copy_diag_kernel(int n, const double* __restrict__ out, double* __restrict__ diag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) diag[i] = out[(int64_t)i * n + i];
+}
+// y = C f, one warp per row (C symmetric, row-major)
+__global__ void __launch_bounds__(256)
+symv_rows_kernel(int N, const double* __restrict__ cov, const double* __restrict__ f, double* __restrict__ y) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= N) return;
+    double acc = 0.0;
+    for (int c = lane_id(); c < N; c += 32) acc = fma(cov[(int64_t)row * N + c], f[c], acc);
+    acc = warp_sum(acc);
+    if (lane_id() == 0) y[row] = acc;
+}
+}  // namespace scb
+
+extern "C" int scb_dcc_from_covariance(int D, int n, const double* cov, int norm, double scale, double* out,
+                                       double* diag_scratch, void* stream) {
+    if (!cov || !out || n < 1 || (D != 1 && D != 3) || (norm && !diag_scratch) || scale == 0.0) return SCB_ERR_INVALID;
+    cudaStream_t st = as_stream(stream);
+    const unsigned grid = (unsigned)ceil_div((int64_t)n * n, 256);
+    scb::dcc_from_cov_kernel<<<grid, 256, 0, st>>>(D, n, cov, scale, out);
+    SCB_LAUNCH_CHECK();
+    if (norm) {
+        scb::copy_diag_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, out, diag_scratch);
+        SCB_LAUNCH_CHECK();
+        scb::dcc_normalise_kernel<<<grid, 256, 0, st>>>(n, diag_scratch, scale, out);
+        SCB_LAUNCH_CHECK();
+    }
+    return SCB_OK;
+}
+
+extern "C" int scb_symv(int N, const double* cov, const double* f, double* y, void* stream) {
+    if (!cov || !f || !y || N < 1) return SCB_ERR_INVALID;
+    scb::symv_rows_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, as_stream(stream)>>>(N, cov, f, y);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
 extern "C" int scb_prs(int n, const double* cov, int norm, double* out, void* stream) {
     if (!cov || !out || n < 1) return SCB_ERR_INVALID;
     prs_kernel<<<(unsigned)ceil_div((int64_t)n * n, 256), 256, 0, as_stream(stream)>>>(n, cov, norm, out);

@@ -32,15 +32,15 @@ def _use_lowest(enm, k_total):
 def _kind(enm, what="GNM/ANM"):
     from .anm import ANM
     from .gnm import GNM
-    if isinstance(enm, GNM):
-        return 1, 1
-    if isinstance(enm, ANM):
-        return 3, 6
+    if isinstance(enm, (GNM, ANM)):
+        enm._sync_exposed()      # in-place edits of a matrix that was handed to the caller (anm.py:53-57)
+        return (1, 1) if isinstance(enm, GNM) else (3, 6)
     raise ValueError(f"Instance of {what} class expected.")
 
 
 def _full_spectrum(enm):
     """(lam[N], modes[N][N]) device tensors of the full decomposition (cached)."""
+    enm._sync_exposed()
     cache = enm._spectrum_cache
     if cache.get("full") is None:
         A = enm._matrix_device().clone()
@@ -137,6 +137,9 @@ def dcc(enm, mode_subset=None, norm=True, tem=None, tem_factors=K_B):
     """nma.py:233-359."""
     D, ntriv = _kind(enm)
     scale = 1.0 if tem is None else tem * tem_factors
+    if mode_subset is None and enm._user_covariance:
+        # the caller assigned the covariance: the reference uses that matrix as is (nma.py:324-336)
+        return _engine.cov_dcc(D, enm._covariance, norm=norm, scale=scale).cpu().numpy()
     if mode_subset is None:
         lam, modes = _pinv_modes(enm)       # == enm.covariance (nma.py:324-336)
     else:
@@ -185,6 +188,9 @@ def linear_response(anm, force, *, mode_subset=None):
         raise ValueError(f"Expected 1D or 2D array, got {force.ndim} dimensions")
     import torch
     from . import _lib
+    if mode_subset is None and anm._user_covariance:
+        # the caller assigned the covariance: nma.py:473 multiplies with exactly that matrix
+        return _engine.cov_matvec(anm._covariance, force.astype(np.float64)).cpu().numpy().reshape(n, 3)
     if mode_subset is None:
         lam, modes = _pinv_modes(anm)
     else:

@@ -704,6 +704,36 @@ def test_setters_and_roundtrip(structures):
         g.kirchhoff = np.zeros((3, 3))
 
 
+def test_matrix_edits_and_assigned_covariance(structures):
+    """anm.py:53-57: `hessian` is returned by reference, so the reference sees in-place edits at the next call;
+    anm.py:138-148 + nma.py:324-336, 473: an assigned covariance is used as is by dcc() and linear_response()."""
+    atoms = atoms_of(structures, "1l2y")
+    anm = sc.ANM(atoms, sc.InvariantForceField(13.0))
+    lam0, _ = anm.eigen()
+    msf0 = anm.mean_square_fluctuation()
+    H = anm.hessian
+    H *= 2.0                                   # in place: no setter involved
+    lam1, _ = anm.eigen()
+    assert np.allclose(lam1[6:], 2.0 * lam0[6:], rtol=1e-10)
+    assert np.allclose(anm.mean_square_fluctuation(), 0.5 * msf0, rtol=1e-8)
+    # a covariance assigned by the caller
+    n = len(atoms.coord)
+    C = 3.0 * sc.ANM(atoms, sc.InvariantForceField(13.0)).covariance
+    other = sc.ANM(atoms, sc.InvariantForceField(13.0))
+    other.covariance = C
+    tr = C.reshape(n, 3, n, 3).trace(axis1=1, axis2=3)
+    d = np.diagonal(tr)
+    assert np.allclose(other.dcc(norm=False), tr, rtol=1e-12)
+    assert np.allclose(other.dcc(), tr / np.sqrt(np.outer(d, d)), rtol=1e-12)
+    assert np.allclose(other.dcc(tem=300), tr / np.sqrt(np.outer(d, d)) * 300 * sc.anm.K_B, rtol=1e-12)
+    f = np.random.default_rng(3).normal(size=(n, 3))
+    assert np.allclose(other.linear_response(f), (C @ f.ravel()).reshape(n, 3), rtol=1e-11, atol=1e-13)
+    g = sc.GNM(atoms, sc.InvariantForceField(7.0))
+    Cg = 2.0 * sc.GNM(atoms, sc.InvariantForceField(7.0)).covariance
+    g.covariance = Cg
+    assert np.allclose(g.dcc(norm=False), Cg, rtol=1e-12)
+
+
 def test_c5_dcc_linear_response():
     """Config C5 scaled down: DMMA W W^T contraction from a mode subset."""
     ref = golden("ref_c5_chain400.npz")
