@@ -9,15 +9,16 @@ cap() {  # name regex skip target
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/${TAG}_$1 python profiles/ncu_targets.py $4 > gpurun_out/${TAG}_$1.log 2>&1
   tail -1 gpurun_out/${TAG}_$1.log
 }
-cap filter resident_filter_kernel 8 c3
-cap lanczos resident_lanczos_kernel 1 c3
-cap build16 resident_build16_kernel 1 c3
-cap spmm64 spmm_paired_kernel 9 c3
-cap gram2 gram2_dmma_kernel 9 c3
-cap rotate rotate_resid_dmma_kernel 9 c3
-cap rr rr_kernel 9 c3
-cap contacts contacts_tiled_kernel 2 c3
-cap assemble assemble_rows_kernel 1 c3
+STEP_PASSES=1 cap filter resident_filter_kernel 0 c3   # first filter launch: all structures, full degree
+STEP_PASSES=1 cap lanczos resident_lanczos_kernel 0 c3
+STEP_PASSES=1 cap build16 resident_build16_kernel 0 c3
+STEP_PASSES=1 cap spmm64 spmm_paired_kernel 0 c3
+STEP_PASSES=1 cap gram2 gram2_dmma_kernel 0 c3
+STEP_PASSES=1 cap rotate rotate_resid_dmma_kernel 0 c3
+STEP_PASSES=1 cap rr rr_kernel 1 c3
+STEP_PASSES=1 cap contacts contacts_tiled_kernel 1 c3
+STEP_PASSES=1 cap assemble assemble_rows_kernel 0 c3
 cap dcc gemm_nt_dmma_kernel 1 dcc
 cap slab dense_slab_apply_kernel 1 slab
+cap tf32 dense_slab_tf32_kernel 1 tf32
 ls -la gpurun_out/${TAG}_*.ncu-rep

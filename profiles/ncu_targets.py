@@ -15,13 +15,13 @@ from springcraft_b200 import _engine
 from springcraft_b200.dense_solver import DenseRowOperator
 from springcraft_b200.ensemble import enm_ensemble_device
 
-what = set(sys.argv[1:]) or {"c3", "dcc", "slab"}
+what = set(sys.argv[1:]) or {"c3", "dcc", "slab", "tf32"}
 if "c3" in what:
     B = int(os.environ.get("STEP_CONF", 4096))
     base, coords, seq = make_ensemble(0, B)
     ff = sc.TabulatedForceField.e_anm(sc.AtomArray(base, *seq))
     xyz = torch.from_numpy(np.ascontiguousarray(coords.transpose(0, 2, 1))).cuda()
-    for _ in range(2):
+    for _ in range(int(os.environ.get("STEP_PASSES", 2))):
         eig, msf, iters, npairs, conv = enm_ensemble_device(xyz, ff, k=20)
     torch.cuda.synchronize()
     print("c3", B, "structures, converged", conv, "outer", float(iters.abs().float().mean()))
@@ -43,3 +43,22 @@ if "slab" in what:
         Y = op.apply(X, X, (0.5, 0.1, 0.25))
     torch.cuda.synchronize()
     print("slab", n, b, float(Y.abs().sum()))
+if "tf32" in what:
+    from springcraft_b200 import _lib
+    h = _lib.require_device()
+    n, b = 8000, 128
+    op = DenseRowOperator(jittered_grid(n, seed=0), sc.ParameterFreeForceField(), 3)
+    N = op.N
+    ld = int(h.scb_tf32_ld(N))
+    hi, lo = op.slab32(True)
+    zc = torch.randn((2 * b, ld), dtype=torch.float32, device="cuda")
+    zp = torch.randn_like(zc)
+    rh = torch.randn((b, ld), dtype=torch.float32, device="cuda")
+    ca = torch.rand(b, device="cuda") * 0.1
+    cb = torch.rand(b, device="cuda")
+    for _ in range(3):
+        _lib.check(h.scb_dense_slab_tf32_apply(N, 0, N, _lib.ptr(hi), _lib.ptr(lo), b, _lib.ptr(zc), _lib.ptr(zp),
+                                               _lib.ptr(rh), _lib.ptr(zp), _lib.ptr(ca), _lib.ptr(cb), 0.7, 1,
+                                               _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    print("tf32 filter step", n, b, float(zp.abs().max()))

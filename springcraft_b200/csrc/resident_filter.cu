@@ -627,7 +627,9 @@ static int launch_lanczos(int B, int n, int b, const int64_t* rowptr, const ResL
     const int nwarps = 4 * ((L.G + 3) / 4);
     const size_t smem = sizeof(float) * ((size_t)3 * 3 * n * COLS + (size_t)nwarps * COLS);
     SCB_CUDA(cudaFuncSetAttribute(resident_lanczos_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(b / COLS), (unsigned)B);
+    // one column group per structure: COLS independent Lanczos runs bound the spectrum as well as b of them
+    (void)b;
+    dim3 grid(1u, (unsigned)B);
     resident_lanczos_kernel<COLS><<<grid, 32 * nwarps, smem, st>>>(n, b, L.G, L.rec_mul, L.rec_pad, rowptr, L.rec,
                                                                   L.gstart, L.order, L.diag32, steps, seed, L.est);
     SCB_LAUNCH_CHECK();
