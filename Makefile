@@ -8,7 +8,7 @@ LIB := springcraft_b200/lib/libscb200.so
 
 all: $(LIB)
 
-build/%.o: springcraft_b200/csrc/%.cu springcraft_b200/csrc/common.cuh springcraft_b200/csrc/subspace.cuh springcraft_b200/csrc/jacobi.cuh springcraft_b200/csrc/paired.cuh springcraft_b200/csrc/resident.cuh include/scb200.h
+build/%.o: springcraft_b200/csrc/%.cu springcraft_b200/csrc/stedc_core.cuh springcraft_b200/csrc/common.cuh springcraft_b200/csrc/subspace.cuh springcraft_b200/csrc/jacobi.cuh springcraft_b200/csrc/paired.cuh springcraft_b200/csrc/resident.cuh include/scb200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -3,7 +3,10 @@
 //
 //  * N <= 64  : one CTA per matrix, two-sided cyclic Jacobi entirely in shared
 //               memory (the Rayleigh-Ritz kernel with S = I).
-//  * N  > 64  : block Jacobi in global memory -- see eig_full_block.cu.
+//  * 64 < N <= 256 : block Jacobi in global memory -- see eig_full_block.cu.
+//  * N > 256  : tridiagonalisation + divide and conquer + back-transformation -- see eig_full_tridiag.cu.
+#include <stdlib.h>
+
 #include "subspace.cuh"
 
 namespace scb {
@@ -11,6 +14,19 @@ namespace scb {
 int eig_full_block(int B, int N, double* A, double* eigval, double* modes, void* workspace, size_t workspace_bytes,
                    cudaStream_t st);
 size_t eig_full_block_workspace_bytes(int B, int N);
+// eig_full_tridiag.cu: Householder tridiagonalisation + divide and conquer + back-transformation
+bool eig_full_tridiag_supported(int N);
+int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st);
+size_t eig_full_tridiag_workspace_bytes(int B, int N);
+
+// SCB_EIG_FULL=jacobi forces the block-Jacobi solver (A/B measurements)
+static bool use_tridiag(int N) {
+    if (!eig_full_tridiag_supported(N)) return false;
+    const char* env = getenv("SCB_EIG_FULL");
+    if (env && env[0] == 'j') return false;
+    return true;
+}
 
 // T[s] = lower triangle of A[s] mirrored, padded to PxP with huge decoupled diagonal; S[s] = I
 __global__ void pad_symmetric_kernel(int N, int P, const double* __restrict__ A, double* __restrict__ T,
@@ -47,6 +63,7 @@ extern "C" size_t scb_eig_full_workspace_bytes(int B, int N) {
         return 3 * (((size_t)B * P * P * sizeof(double) + 255) & ~size_t(255)) +
                (((size_t)B * P * sizeof(double) + 255) & ~size_t(255)) + 256;
     }
+    if (use_tridiag(N)) return eig_full_tridiag_workspace_bytes(B, N);
     return eig_full_block_workspace_bytes(B, N);
 }
 
@@ -54,6 +71,7 @@ extern "C" int scb_eig_full(int B, int N, double* A, double* eigval, double* mod
                             size_t workspace_bytes, void* stream) {
     if (!A || !eigval || !modes || !workspace || B < 1 || N < 1) return SCB_ERR_INVALID;
     cudaStream_t st = as_stream(stream);
+    if (N > 64 && use_tridiag(N)) return eig_full_tridiag(B, N, A, eigval, modes, workspace, workspace_bytes, st);
     if (N > 64) return eig_full_block(B, N, A, eigval, modes, workspace, workspace_bytes, st);
     const int P = N <= 32 ? 32 : 64;
     Arena ar(workspace, workspace_bytes);

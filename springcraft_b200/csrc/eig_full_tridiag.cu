@@ -1,0 +1,999 @@
+// K3c (N > 128): full symmetric eigendecomposition by reduction to tridiagonal
+// form, divide and conquer on the tridiagonal matrix, and back-transformation.
+// Replaces LAPACK dsyevd behind np.linalg.eigh (nma.py:61) and np.linalg.pinv
+// (anm.py:135) when every mode is requested; the two-sided block Jacobi of
+// eig_full_block.cu (145 N^3 flop) stays for small orders only.
+//
+//  1. sytrd_kernel -- Householder tridiagonalisation, ONE persistent
+//     cooperative launch.  The rows of the (full, symmetric) matrix are dealt
+//     cyclically to the G CTAs of a group; per column j a CTA applies the
+//     rank-2 update of reflector j-1 to its rows and multiplies the updated
+//     rows with reflector j in the same pass (one read + one write of the
+//     trailing matrix per column), writes its slice of p = tau A v and of the
+//     next column, and meets the group at ONE flag barrier; every CTA then
+//     forms w, the next column and the next reflector redundantly from the
+//     exchanged 2 x N doubles.  Rows live in shared memory as far as they fit
+//     (re-packed every 128 columns as the trailing matrix shrinks), the rest is
+//     served from L2: the reduction never streams the matrix from HBM.  Groups
+//     of CTAs work on different matrices of a batch concurrently.
+//  2. divide and conquer (stedc_core.cuh): leaves of order <= 64 by Jacobi in
+//     shared memory, then per level  prepare (rank sort + deflation scan) ->
+//     rotate -> secular roots (warp per root) -> z-hat -> eigenvector matrix
+//     of the rank-one problem -> Z_new = U^T Z as FP64 tensor-core GEMMs
+//     (all merges of a level and all matrices of a batch in one launch each).
+//  3. back-transformation X <- X (I - V T V^T) by compact-WY blocks of 128
+//     reflectors: three DMMA GEMMs per block.
+// No host synchronisation anywhere: every data-dependent size (survivors of a
+// deflation, rotations) stays on the device.
+#include <cooperative_groups.h>
+
+#include "jacobi.cuh"
+#include "stedc_core.cuh"
+#include "subspace.cuh"
+
+namespace scb {
+
+// ------------------------------------------------------------------------------------------------------------
+// general FP64 tensor-core GEMM: C[M][N] = alpha * op(A) op(B) + beta * C, row-major C
+//   AK: A is K-major  A[m*lda + k]   else M-major  A[k*lda + m]
+//   BK: B is K-major  B[n*ldb + k]   else N-major  B[k*ldb + n], optionally with gathered rows  B[bidx[k]*ldb + n]
+// Leading dimensions and the offsets of the operand origins must be even (16-byte cp.async chunks).
+// ------------------------------------------------------------------------------------------------------------
+struct GemmTask {
+    const double* A;
+    const double* B;
+    double* C;
+    const int32_t* bidx;
+    int M, N, K;
+    int lda, ldb, ldc;
+    double alpha, beta;
+};
+
+namespace {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// copies `bytes` (0, 8 or 16) and zero-fills the rest of the 16-byte chunk
+__device__ __forceinline__ void cp_async16z(void* smem, const void* gmem, int bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
+constexpr int kTM = 128, kTN = 128, kTK = 16;
+constexpr int kLDK = 20;    // K-major tile: [128][20]
+constexpr int kLDM = 136;   // M/N-major tile: [16][136]
+constexpr int kTileDoubles = kTM * kLDK;   // 2560 >= 16 * 136
+constexpr size_t kGemmSmem = sizeof(double) * 4 * kTileDoubles;
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(256)
+dgemm_dmma_kernel(GemmTask single, const GemmTask* __restrict__ tasks, int64_t strideA, int64_t strideB,
+                  int64_t strideC) {
+    GemmTask t;
+    if (tasks) t = tasks[blockIdx.z];
+    else {
+        t = single;
+        t.A += strideA * blockIdx.z; t.B += strideB * blockIdx.z; t.C += strideC * blockIdx.z;
+    }
+    const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+    if (m0 >= t.M || n0 >= t.N) return;
+    extern __shared__ __align__(16) double gsm[];
+    double* sA = gsm;                      // [2][kTileDoubles]
+    double* sB = gsm + 2 * kTileDoubles;   // [2][kTileDoubles]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps, warp tile 32 x 64
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto load_stage = [&](int stage, int kk) {
+        double* a_s = sA + stage * kTileDoubles;
+        double* b_s = sB + stage * kTileDoubles;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = tid + q * 256;
+            if (AK) {
+                const int r = c >> 3, kc = (c & 7) * 2;
+                const int kg = kk + kc;
+                int bytes = 0;
+                if (m0 + r < t.M && kg < t.K) bytes = (kg + 1 < t.K) ? 16 : 8;
+                cp_async16z(&a_s[r * kLDK + kc], bytes ? (const void*)(t.A + (int64_t)(m0 + r) * t.lda + kg) : (const void*)t.A, bytes);
+            } else {
+                const int kr = c >> 6, mc = (c & 63) * 2;
+                int bytes = 0;
+                if (kk + kr < t.K && m0 + mc < t.M) bytes = (m0 + mc + 1 < t.M) ? 16 : 8;
+                cp_async16z(&a_s[kr * kLDM + mc], bytes ? (const void*)(t.A + (int64_t)(kk + kr) * t.lda + m0 + mc) : (const void*)t.A, bytes);
+            }
+            if (BK) {
+                const int r = c >> 3, kc = (c & 7) * 2;
+                const int kg = kk + kc;
+                int bytes = 0;
+                if (n0 + r < t.N && kg < t.K) bytes = (kg + 1 < t.K) ? 16 : 8;
+                cp_async16z(&b_s[r * kLDK + kc], bytes ? (const void*)(t.B + (int64_t)(n0 + r) * t.ldb + kg) : (const void*)t.B, bytes);
+            } else {
+                const int kr = c >> 6, nc = (c & 63) * 2;
+                int bytes = 0;
+                if (kk + kr < t.K && n0 + nc < t.N) bytes = (n0 + nc + 1 < t.N) ? 16 : 8;
+                const double* src = t.B;
+                if (bytes) {
+                    const int64_t row = t.bidx ? (int64_t)t.bidx[kk + kr] : (int64_t)(kk + kr);
+                    src = t.B + row * t.ldb + n0 + nc;
+                }
+                cp_async16z(&b_s[kr * kLDM + nc], src, bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    const int nk = (t.K + kTK - 1) / kTK;
+    if (nk > 0) load_stage(0, 0);
+    for (int it = 0; it < nk; ++it) {
+        const int stage = it & 1;
+        if (it + 1 < nk) {
+            load_stage(stage ^ 1, (it + 1) * kTK);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        }
+        __syncthreads();
+        const double* a_s = sA + stage * kTileDoubles;
+        const double* b_s = sB + stage * kTileDoubles;
+#pragma unroll
+        for (int k4 = 0; k4 < kTK; k4 += 4) {
+            double af[4], bf[8];
+            const int kq = k4 + (lane & 3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = wm * 32 + i * 8 + (lane >> 2);
+                af[i] = AK ? a_s[r * kLDK + kq] : a_s[kq * kLDM + r];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cidx = wn * 64 + j * 8 + (lane >> 2);
+                bf[j] = BK ? b_s[cidx * kLDK + kq] : b_s[kq * kLDM + cidx];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + wm * 32 + i * 8 + (lane >> 2);
+        if (r >= t.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = n0 + wn * 64 + j * 8 + 2 * (lane & 3);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (c + e >= t.N) continue;
+                double* dst = t.C + (int64_t)r * t.ldc + c + e;
+                double v = t.alpha * acc[i][j][e];
+                if (t.beta != 0.0) v += t.beta * *dst;
+                *dst = v;
+            }
+        }
+    }
+}
+
+template <bool AK, bool BK>
+int launch_gemm(const GemmTask& single, const GemmTask* tasks, int maxM, int maxN, int batch, int64_t sA, int64_t sB,
+                int64_t sC, cudaStream_t st) {
+    if (maxM < 1 || maxN < 1 || batch < 1) return SCB_OK;
+    SCB_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    dim3 grid((unsigned)ceil_div(maxN, kTN), (unsigned)ceil_div(maxM, kTM), (unsigned)batch);
+    dgemm_dmma_kernel<AK, BK><<<grid, 256, kGemmSmem, st>>>(single, tasks, sA, sB, sC);
+    SCB_LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 1. tridiagonalisation
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTrdThreads = 1024;
+constexpr int kTrdEpoch = 128;   // columns between two re-packings of the shared-memory row cache
+
+struct TrdParams {
+    int N, LD, B, G, ngroups;
+    int cache_doubles;   // capacity of the row cache in doubles
+    double* A;           // [B][N][LD] full symmetric matrix (destroyed)
+    double* Vt;          // [B][N][LD] row j = reflector j (zero up to j, 1 at j+1); zeroed by the caller
+    double* tau;         // [B][LD]
+    double* d;           // [B][LD]
+    double* e;           // [B][LD]
+    double* xch;         // [ngroups][2][2][LD]  (p, next column) of even / odd steps
+    unsigned* flags;     // [ngroups][G] barrier epochs, zeroed by the caller
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// all CTAs of a group: every CTA publishes its epoch, one thread per member CTA waits for that member
+__device__ __forceinline__ void group_barrier(unsigned* flags, int me, int G, unsigned epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release_u32(flags + me, epoch);
+    }
+    if ((int)threadIdx.x < G) {
+        while (ld_acquire_u32(flags + threadIdx.x) < epoch) {}
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTrdThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
+    extern __shared__ __align__(16) double tsm[];
+    __shared__ double red[kTrdThreads / 32];
+    const int N = P.N, LD = P.LD, G = P.G;
+    const int grp = blockIdx.x / G, c = blockIdx.x % G;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* vprev = tsm;
+    double* wprev = tsm + LD;
+    double* vcur = tsm + 2 * LD;
+    double* cache = tsm + 3 * LD;
+    unsigned* flags = P.flags + (size_t)grp * G;
+    double* xch = P.xch + (size_t)grp * 4 * LD;
+    unsigned epoch = 0;
+    const int nown = (c < N) ? (N - c + G - 1) / G : 0;   // rows c, c+G, ...
+
+    for (int s = grp; s < P.B; s += P.ngroups) {
+        double* A = P.A + (size_t)s * N * LD;
+        double* Vt = P.Vt + (size_t)s * N * LD;
+        double* tau = P.tau + (size_t)s * LD;
+        double* dd = P.d + (size_t)s * LD;
+        double* ee = P.e + (size_t)s * LD;
+        int cache_col0 = 0, cache_len = LD, cache_rows = 0;
+        double tau_prev = 0.0;
+
+        for (int j = 0; j < N; ++j) {
+            // ---- re-pack the row cache: rows are only needed from column j+1 on
+            if ((j % kTrdEpoch) == 0 && j + 1 < N) {
+                for (int q = warp; q < cache_rows; q += kTrdThreads / 32) {   // write back
+                    const int r = nown - 1 - q;
+                    double* dst = A + (size_t)(c + G * r) * LD;
+                    const double* src = cache + (size_t)q * cache_len - cache_col0;
+                    for (int cc = cache_col0 + lane; cc < LD; cc += 32) dst[cc] = src[cc];
+                }
+                __syncthreads();
+                cache_col0 = (j + 1) & ~1;
+                cache_len = LD - cache_col0;
+                const int rmin = (j + 1 > c) ? (j + 1 - c + G - 1) / G : 0;   // first owned row with index > j
+                int alive = nown - rmin;
+                if (alive < 0) alive = 0;
+                cache_rows = P.cache_doubles / cache_len;
+                if (cache_rows > alive) cache_rows = alive;
+                for (int q = warp; q < cache_rows; q += kTrdThreads / 32) {
+                    const int r = nown - 1 - q;
+                    const double* src = A + (size_t)(c + G * r) * LD;
+                    double* dst = cache + (size_t)q * cache_len - cache_col0;
+                    for (int cc = cache_col0 + lane; cc < LD; cc += 32) dst[cc] = src[cc];
+                }
+                __syncthreads();
+            }
+            // ---- phase 1 (every CTA, redundantly): w_{j-1}, d_j, column j, reflector j
+            double dj;
+            if (j == 0) {
+                for (int i = tid; i < N; i += kTrdThreads) vcur[i] = A[(size_t)i * LD];
+                __syncthreads();
+                dj = vcur[0];
+            } else {
+                const double* pbuf = xch + (size_t)((j - 1) & 1) * 2 * LD;
+                const double* cbuf = pbuf + LD;
+                double acc = 0.0;
+                for (int i = j + tid; i < N; i += kTrdThreads) {
+                    const double p = __ldcg(pbuf + i);
+                    wprev[i] = p;
+                    acc += p * vprev[i];
+                }
+                const double dot = block_sum_1024(acc, red);
+                const double kappa = 0.5 * tau_prev * dot;
+                for (int i = j + tid; i < N; i += kTrdThreads) wprev[i] -= kappa * vprev[i];
+                __syncthreads();
+                const double wj = wprev[j];
+                dj = __ldcg(cbuf + j) - 2.0 * wj;   // vprev[j] == 1
+                for (int i = j + 1 + tid; i < N; i += kTrdThreads)
+                    vcur[i] = __ldcg(cbuf + i) - (vprev[i] * wj + wprev[i]);
+                __syncthreads();
+            }
+            double tau_cur = 0.0, beta = 0.0;
+            if (j < N - 1) {
+                const double x0 = vcur[j + 1];
+                beta = x0;
+                if (j < N - 2) {
+                    double acc = 0.0;
+                    for (int i = j + 2 + tid; i < N; i += kTrdThreads) acc += vcur[i] * vcur[i];
+                    const double sigma = block_sum_1024(acc, red);
+                    if (sigma > 0.0) {
+                        const double nrm = sqrt(x0 * x0 + sigma);
+                        beta = -copysign(nrm, x0);
+                        tau_cur = (beta - x0) / beta;
+                        const double scal = 1.0 / (x0 - beta);
+                        for (int i = j + 2 + tid; i < N; i += kTrdThreads) vcur[i] *= scal;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) vcur[j + 1] = 1.0;
+                __syncthreads();
+            }
+            if ((j % G) == c) {
+                if (tid == 0) {
+                    dd[j] = dj;
+                    if (j < N - 1) { ee[j] = beta; tau[j] = tau_cur; }
+                }
+                if (j < N - 1)
+                    for (int i = j + 1 + tid; i < N; i += kTrdThreads) Vt[(size_t)j * LD + i] = vcur[i];
+            }
+            if (j == N - 1) break;
+            // ---- pass j: rows i > j of this CTA: apply update j-1, multiply with reflector j
+            {
+                double* pout = xch + (size_t)(j & 1) * 2 * LD;
+                double* cout = pout + LD;
+                const int rmin = (j + 1 > c) ? (j + 1 - c + G - 1) / G : 0;
+                for (int r = rmin + warp; r < nown; r += kTrdThreads / 32) {
+                    const int i = c + G * r;
+                    const int q = nown - 1 - r;
+                    double* rowp = (q < cache_rows) ? cache + (size_t)q * cache_len - cache_col0 : A + (size_t)i * LD;
+                    double acc = 0.0, col1 = 0.0;
+                    if (j > 0) {
+                        const double vi = vprev[i], wi = wprev[i];
+#pragma unroll 4
+                        for (int cc = j + 1 + lane; cc < N; cc += 32) {
+                            const double a = rowp[cc] - (vi * wprev[cc] + wi * vprev[cc]);
+                            rowp[cc] = a;
+                            acc = fma(a, vcur[cc], acc);
+                            if (cc == j + 1) col1 = a;
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int cc = 1 + lane; cc < N; cc += 32) {
+                            const double a = rowp[cc];
+                            acc = fma(a, vcur[cc], acc);
+                            if (cc == 1) col1 = a;
+                        }
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) {
+                        __stcg(pout + i, tau_cur * acc);
+                        __stcg(cout + i, col1);
+                    }
+                }
+            }
+            ++epoch;
+            group_barrier(flags, c, G, epoch);
+            double* tmp = vprev; vprev = vcur; vcur = tmp;
+            tau_prev = tau_cur;
+        }
+        ++epoch;
+        group_barrier(flags, c, G, epoch);   // the exchange buffers are reused by the next matrix of this group
+    }
+}
+
+// Ap[s][i][j] = symmetric extension of the lower triangle of A[s] (N x N), padded to LD columns with zeros
+__global__ void trd_init_kernel(int N, int LD, const double* __restrict__ A, double* __restrict__ Ap) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)N * LD) return;
+    const int i = (int)(q / LD), j = (int)(q % LD);
+    const double* As = A + (int64_t)blockIdx.y * N * N;
+    double v = 0.0;
+    if (j < N) v = (j <= i) ? As[(int64_t)i * N + j] : As[(int64_t)j * N + i];
+    Ap[(int64_t)blockIdx.y * N * LD + q] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 2. divide and conquer on the tridiagonal matrix
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kLeaf = 64;
+
+// node t of `level` (root = level 0) covers [lo, hi); all split points are even (16-byte aligned operand origins)
+__host__ __device__ inline void node_range(int N, int level, int t, int* lo, int* hi) {
+    int a = 0, b = N;
+    for (int bit = level - 1; bit >= 0; --bit) {
+        const int mid = a + (((b - a) / 2) & ~1);
+        if ((t >> bit) & 1) a = mid; else b = mid;
+    }
+    *lo = a;
+    *hi = b;
+}
+
+struct DcWork {           // per matrix (index s) unless noted; vectors have LD entries
+    int N, LD, L;
+    double *d, *e;        // tridiagonal (d is torn in place, e replaced by |e|)
+    double* sgn;          // row signs that make all off-diagonals non-negative
+    double *D0, *D1;      // eigenvalues of the current / next level, per sub-problem range
+    double *Z0, *Z1;      // [N][LD] eigenvectors as rows, block diagonal over the sub-problems
+    double* U;            // [N][LD] differences d_i - lambda_j, then the eigenvectors of the rank-one problems
+    double *dsc, *dl, *w, *zh;
+    int32_t *nd, *dfl;    // survivors / deflated entries (local indices) per range
+    stedc::Rotation* rot;
+    int32_t *kc, *nr;     // [B][nodes of the level] survivors and rotations of each merge
+    GemmTask* tasks;      // [B * nodes]
+    int64_t vstride, mstride;   // strides between matrices of the batch for vectors / matrices
+};
+
+// |e|, signs, tearing of every boundary of every level
+__global__ void __launch_bounds__(1024) dc_setup_kernel(DcWork W) {
+    const int s = blockIdx.x, N = W.N;
+    double* d = W.d + s * W.vstride;
+    double* e = W.e + s * W.vstride;
+    double* sgn = W.sgn + s * W.vstride;
+    // sgn[i] = (-1)^(number of negative off-diagonals before i)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int neg = 0;
+        for (int q = 0; q < i; ++q) neg += (e[q] < 0.0) ? 1 : 0;
+        sgn[i] = (neg & 1) ? -1.0 : 1.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i + 1 < N; i += blockDim.x) e[i] = fabs(e[i]);
+    __syncthreads();
+    for (int level = 1; level <= W.L; ++level)
+        for (int t = 1 + 2 * threadIdx.x; t < (1 << level); t += 2 * blockDim.x) {
+            int lo, hi;
+            node_range(N, level, t, &lo, &hi);
+            const double b = e[lo - 1];
+            d[lo - 1] -= b;
+            d[lo] -= b;
+        }
+}
+
+__global__ void __launch_bounds__(512) dc_leaf_kernel(DcWork W) {
+    constexpr int LDS = kLeaf + 1;
+    constexpr int NT = 512;
+    extern __shared__ __align__(16) double lsm[];
+    double* S = lsm;
+    double* V = lsm + kLeaf * LDS;
+    __shared__ double cs[kLeaf], sn[kLeaf], red[NT / 32];
+    __shared__ int pp[kLeaf], qq[kLeaf];
+    const int s = blockIdx.y, N = W.N, LD = W.LD;
+    int lo, hi;
+    node_range(N, W.L, blockIdx.x, &lo, &hi);
+    const int n = hi - lo;
+    const double* d = W.d + s * W.vstride;
+    const double* e = W.e + s * W.vstride;
+    for (int q = threadIdx.x; q < kLeaf * kLeaf; q += NT) {
+        const int r = q / kLeaf, cidx = q % kLeaf;
+        double v = 0.0;
+        if (r < n && cidx < n) {
+            if (r == cidx) v = d[lo + r];
+            else if (r == cidx + 1) v = e[lo + cidx];
+            else if (cidx == r + 1) v = e[lo + r];
+        }
+        S[r * LDS + cidx] = v;
+        V[r * LDS + cidx] = (r == cidx) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    jacobi_eigen_smem<kLeaf, LDS, NT>(S, V, cs, sn, pp, qq, red, 60, false);
+    double* D = W.D0 + s * W.vstride;
+    double* Z = W.Z0 + s * W.mstride;
+    for (int q = threadIdx.x; q < n * n; q += NT) {
+        const int m = q / n, i = q % n;
+        Z[(int64_t)(lo + m) * LD + lo + i] = V[i * LDS + m];
+    }
+    for (int m = threadIdx.x; m < n; m += NT) D[lo + m] = S[m * LDS + m];
+}
+
+// one CTA per merge: z, rank sort, deflation scan, GEMM task
+__global__ void __launch_bounds__(1024)
+dc_prepare_kernel(DcWork W, int level, const double* __restrict__ Dcur, const double* __restrict__ Zcur,
+                  double* __restrict__ Znew) {
+    extern __shared__ __align__(16) double psm[];
+    const int s = blockIdx.y, t = blockIdx.x, N = W.N, LD = W.LD;
+    const int nodes = 1 << level;
+    int lo, hi, l1, mid;
+    node_range(N, level, t, &lo, &hi);
+    node_range(N, level + 1, 2 * t, &l1, &mid);
+    const int n = hi - lo;
+    double* dd = psm;                      // [n]
+    double* z = psm + n;                   // [n]
+    int* order = reinterpret_cast<int*>(psm + 2 * n);   // [n]
+    const double* D = Dcur + s * W.vstride;
+    const double* Z = Zcur + s * W.mstride;
+    const double rho = 2.0 * W.e[s * W.vstride + mid - 1];
+    for (int l = threadIdx.x; l < n; l += blockDim.x) {
+        dd[l] = D[lo + l];
+        z[l] = Z[(int64_t)(lo + l) * LD + (lo + l < mid ? mid - 1 : mid)] * 0.70710678118654752440;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < n; l += blockDim.x) {
+        const double v = dd[l];
+        int r = 0;
+        for (int q = 0; q < n; ++q) {
+            const double u = dd[q];
+            r += (u < v) || (u == v && q < l);
+        }
+        order[r] = l;
+    }
+    __syncthreads();
+    int32_t* nd = W.nd + s * W.vstride + lo;
+    int32_t* dfl = W.dfl + s * W.vstride + lo;
+    stedc::Rotation* rot = W.rot + s * W.vstride + lo;
+    __shared__ int sh_k;
+    if (threadIdx.x == 0) {
+        int nrot = 0;
+        const int k = stedc::deflation_scan(n, order, dd, z, rho, nd, dfl, rot, &nrot);
+        sh_k = k;
+        W.kc[s * nodes + t] = k;
+        W.nr[s * nodes + t] = nrot;
+        GemmTask g;
+        g.A = W.U + s * W.mstride + (int64_t)lo * LD + lo;
+        g.B = Z + (int64_t)lo * LD + lo;
+        g.C = Znew + s * W.mstride + (int64_t)lo * LD + lo;
+        g.bidx = nd;
+        g.M = k; g.N = n; g.K = k;
+        g.lda = LD; g.ldb = LD; g.ldc = LD;
+        g.alpha = 1.0; g.beta = 0.0;
+        W.tasks[s * nodes + t] = g;
+    }
+    __syncthreads();
+    const int k = sh_k;
+    double* dl = W.dl + s * W.vstride + lo;
+    double* w = W.w + s * W.vstride + lo;
+    double* dsc = W.dsc + s * W.vstride + lo;
+    for (int l = threadIdx.x; l < n; l += blockDim.x) {
+        dsc[l] = dd[l];
+        if (l < k) {
+            const int src = nd[l];
+            dl[l] = dd[src];
+            w[l] = z[src];
+        }
+    }
+}
+
+// rotations of the deflation scan, applied to the eigenvector rows: one thread per component
+__global__ void __launch_bounds__(256) dc_rotate_kernel(DcWork W, int level, double* __restrict__ Zcur) {
+    const int s = blockIdx.z, t = blockIdx.y, LD = W.LD;
+    const int nodes = 1 << level;
+    const int nrot = W.nr[s * nodes + t];
+    if (nrot == 0) return;
+    int lo, hi;
+    node_range(W.N, level, t, &lo, &hi);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi - lo) return;
+    const stedc::Rotation* rot = W.rot + s * W.vstride + lo;
+    double* Z = Zcur + s * W.mstride + (int64_t)lo * LD + lo + i;
+    for (int r = 0; r < nrot; ++r) {
+        const stedc::Rotation R = rot[r];
+        const double a = Z[(int64_t)R.p * LD], b = Z[(int64_t)R.q * LD];
+        Z[(int64_t)R.p * LD] = R.c * a + R.s * b;
+        Z[(int64_t)R.q * LD] = R.c * b - R.s * a;
+    }
+}
+
+struct WarpLanes {
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ double sum(double v) const { return warp_sum(v); }
+};
+
+// one warp per root of the secular equation
+__global__ void __launch_bounds__(256) dc_secular_kernel(DcWork W, int level, double* __restrict__ Dnew) {
+    const int s = blockIdx.z, t = blockIdx.y, LD = W.LD;
+    const int nodes = 1 << level;
+    const int k = W.kc[s * nodes + t];
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= k) return;
+    int lo, hi, l1, mid;
+    node_range(W.N, level, t, &lo, &hi);
+    node_range(W.N, level + 1, 2 * t, &l1, &mid);
+    const double rho = 2.0 * W.e[s * W.vstride + mid - 1];
+    const double* dl = W.dl + s * W.vstride + lo;
+    const double* w = W.w + s * W.vstride + lo;
+    double* delta = W.U + s * W.mstride + (int64_t)(lo + j) * LD + lo;
+    WarpLanes cx;
+    const double lam = stedc::secular_root(cx, k, j, dl, w, rho, delta);
+    if ((threadIdx.x & 31) == 0) Dnew[s * W.vstride + lo + j] = lam;
+}
+
+// z-hat_i = sign(w_i) sqrt( prod_j (dl_i - lam_j) / prod_{j != i} (dl_i - dl_j) ): 32 components x 32 slices of j
+__global__ void __launch_bounds__(1024) dc_zhat_kernel(DcWork W, int level) {
+    __shared__ double part[32][33];
+    const int s = blockIdx.z, t = blockIdx.y, LD = W.LD;
+    const int nodes = 1 << level;
+    const int k = W.kc[s * nodes + t];
+    if ((int)blockIdx.x * 32 >= k) return;
+    int lo, hi;
+    node_range(W.N, level, t, &lo, &hi);
+    const int ix = threadIdx.x & 31, jy = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + ix;
+    const double* dl = W.dl + s * W.vstride + lo;
+    const double* U = W.U + s * W.mstride + (int64_t)lo * LD + lo;
+    double p = 1.0;
+    if (i < k) {
+        const double di = dl[i];
+        for (int j = jy; j < k; j += 32) {
+            const double num = U[(int64_t)j * LD + i];
+            p *= (j == i) ? num : num / (di - dl[j]);
+        }
+    }
+    part[jy][ix] = p;
+    __syncthreads();
+    if (jy == 0 && i < k) {
+        double q = 1.0;
+        for (int y = 0; y < 32; ++y) q *= part[y][ix];
+        W.zh[s * W.vstride + lo + i] = copysign(sqrt(fabs(q)), W.w[s * W.vstride + lo + i]);
+    }
+}
+
+// U[j][i] = zh_i / (dl_i - lam_j), normalised: one warp per root
+__global__ void __launch_bounds__(256) dc_vectors_kernel(DcWork W, int level) {
+    const int s = blockIdx.z, t = blockIdx.y, LD = W.LD;
+    const int nodes = 1 << level;
+    const int k = W.kc[s * nodes + t];
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= k) return;
+    int lo, hi;
+    node_range(W.N, level, t, &lo, &hi);
+    const int lane = threadIdx.x & 31;
+    const double* zh = W.zh + s * W.vstride + lo;
+    double* row = W.U + s * W.mstride + (int64_t)(lo + j) * LD + lo;
+    double acc = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        const double u = zh[i] / row[i];
+        row[i] = u;
+        acc += u * u;
+    }
+    acc = warp_sum(acc);
+    const double sc = 1.0 / sqrt(acc);
+    for (int i = lane; i < k; i += 32) row[i] *= sc;
+}
+
+// deflated eigenpairs are copied behind the k new ones
+__global__ void __launch_bounds__(128)
+dc_copy_deflated_kernel(DcWork W, int level, const double* __restrict__ Zcur, double* __restrict__ Znew,
+                        double* __restrict__ Dnew) {
+    const int s = blockIdx.z, t = blockIdx.y, LD = W.LD;
+    const int nodes = 1 << level;
+    const int k = W.kc[s * nodes + t];
+    int lo, hi;
+    node_range(W.N, level, t, &lo, &hi);
+    const int n = hi - lo;
+    const int q = blockIdx.x;
+    if (q >= n - k) return;
+    const int src = W.dfl[s * W.vstride + lo + q];
+    const double* from = Zcur + s * W.mstride + (int64_t)(lo + src) * LD + lo;
+    double* to = Znew + s * W.mstride + (int64_t)(lo + k + q) * LD + lo;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) to[i] = from[i];
+    if (threadIdx.x == 0) Dnew[s * W.vstride + lo + k + q] = W.dsc[s * W.vstride + lo + src];
+}
+
+// ascending rank of every eigenvalue (ties by index); eigval[rank] = D
+__global__ void __launch_bounds__(256)
+dc_rank_kernel(int N, int64_t vstride, const double* __restrict__ D, int32_t* __restrict__ rank,
+               double* __restrict__ eigval) {
+    const int s = blockIdx.y;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= N) return;
+    const double* Ds = D + s * vstride;
+    const double v = Ds[m];
+    int r = 0;
+    for (int q = 0; q < N; ++q) {
+        const double u = Ds[q];
+        r += (u < v) || (u == v && q < m);
+    }
+    rank[s * vstride + m] = r;
+    eigval[(int64_t)s * N + r] = v;
+}
+
+// X[rank[m]][i] = sgn[i] * Z[m][i]
+__global__ void __launch_bounds__(256)
+dc_permute_kernel(int N, int LD, int64_t vstride, int64_t mstride, const double* __restrict__ Z,
+                  const int32_t* __restrict__ rank, const double* __restrict__ sgn, double* __restrict__ X) {
+    const int s = blockIdx.z, m = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LD) return;
+    const int r = rank[s * vstride + m];
+    X[s * mstride + (int64_t)r * LD + i] = (i < N) ? sgn[s * vstride + i] * Z[s * mstride + (int64_t)m * LD + i] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 3. back-transformation
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kWY = 128;   // reflectors per compact-WY block
+
+// T of the block  H_j0 ... H_j0+nb-1 = I - V T V^T  (forward, columnwise): T[a][a] = tau_a,
+// T[0:a, a] = -tau_a T[0:a, 0:a] (V^T v_a)[0:a].  One CTA per block; Gm = V^T V of the block.
+__global__ void __launch_bounds__(256)
+wy_tfactor_kernel(int N, int64_t vstride, int nblk, const double* __restrict__ tau, const double* __restrict__ Gm,
+                  double* __restrict__ T) {
+    extern __shared__ __align__(16) double wsm[];   // T [kWY][kWY+1]
+    constexpr int LDT = kWY + 1;
+    __shared__ double col[kWY];
+    const int s = blockIdx.y, b = blockIdx.x;
+    const int j0 = b * kWY;
+    const int nb = min(kWY, (N - 1) - j0);   // reflectors j0 .. j0+nb-1 (there are N-1, the last has tau = 0)
+    const double* G = Gm + ((int64_t)s * nblk + b) * kWY * kWY;
+    double* Tg = T + ((int64_t)s * nblk + b) * kWY * kWY;
+    const double* tv = tau + s * vstride + j0;
+    for (int q = threadIdx.x; q < kWY * LDT; q += blockDim.x) wsm[q] = 0.0;
+    __syncthreads();
+    for (int a = 0; a < nb; ++a) {
+        const double ta = tv[a];
+        // col[r] = -ta * sum_{c=r}^{a-1} T[r][c] G[c][a]   (T upper triangular)
+        for (int r = threadIdx.x; r < a; r += blockDim.x) {
+            double acc = 0.0;
+            for (int cidx = r; cidx < a; ++cidx) acc = fma(wsm[r * LDT + cidx], G[(int64_t)cidx * kWY + a], acc);
+            col[r] = -ta * acc;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < a; r += blockDim.x) wsm[r * LDT + a] = col[r];
+        if (threadIdx.x == 0) wsm[a * LDT + a] = ta;
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < kWY * kWY; q += blockDim.x) Tg[q] = wsm[(q / kWY) * LDT + q % kWY];
+}
+
+// GEMM tasks of the Gram matrices Gm[b] = V_b V_b^T of all blocks and matrices
+__global__ void wy_gram_tasks_kernel(int N, int LD, int nblk, int live, int64_t mstride, const double* __restrict__ Vt,
+                                     double* __restrict__ Gm, GemmTask* __restrict__ tasks) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nblk * live) return;
+    const int s = q / nblk, b = q % nblk;
+    const int j0 = b * kWY;
+    const int nb = min(kWY, N - 1 - j0);
+    GemmTask g;
+    g.A = Vt + s * mstride + (int64_t)j0 * LD + j0;   // the reflectors of this block vanish below component j0+1
+    g.B = g.A;
+    g.C = Gm + (int64_t)q * kWY * kWY;
+    g.bidx = nullptr;
+    g.M = nb; g.N = nb; g.K = N - j0;
+    g.lda = LD; g.ldb = LD; g.ldc = kWY;
+    g.alpha = 1.0; g.beta = 0.0;
+    tasks[q] = g;
+}
+
+// modes[s][m][i] = X[s][m][i]
+__global__ void __launch_bounds__(256)
+export_rows_kernel(int N, int LD, int64_t mstride, const double* __restrict__ X, double* __restrict__ modes) {
+    const int s = blockIdx.z, m = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    modes[((int64_t)s * N + m) * N + i] = X[s * mstride + (int64_t)m * LD + i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct TrdPlan {
+    int LD, L, G, ngroups, group, nblk, cache_doubles;
+    size_t smem;
+};
+
+int dc_levels(int N) {
+    int L = 0, n = N;
+    while (n > kLeaf) {
+        n = n - ((n / 2) & ~1);   // the larger child
+        ++L;
+    }
+    return L;
+}
+
+constexpr size_t kTrdSmemBudget = 220 * 1024;
+
+TrdPlan make_plan(int B, int N) {
+    TrdPlan p;
+    p.LD = (N + 3) & ~3;
+    p.L = dc_levels(N);
+    p.nblk = (int)ceil_div(N - 1, kWY);
+    // matrices that share the launches of the batched stages: as many as fit ~3 GB of workspace, at most 64
+    const size_t per = sizeof(double) * 4 * (size_t)N * p.LD;
+    size_t g = ((size_t)3 << 30) / per;
+    if (g < 1) g = 1;
+    if (g > 64) g = 64;
+    p.group = (int)(g < (size_t)B ? g : (size_t)B);
+    // CTA groups of the tridiagonalisation: more groups (fewer CTAs per matrix) as long as all rows of a CTA stay in
+    // shared memory; a single matrix always gets every SM
+    p.ngroups = 1;
+    const size_t vec = sizeof(double) * 3 * p.LD;
+    for (int ng = 2; ng <= 8 && ng <= p.group; ng *= 2) {
+        const int G = kNumSM / ng;
+        const size_t rows = (size_t)ceil_div(N, G) * p.LD * sizeof(double);
+        if (vec + rows <= kTrdSmemBudget) p.ngroups = ng;
+    }
+    p.G = kNumSM / p.ngroups;
+    if (p.G > N) p.G = N;
+    p.smem = kTrdSmemBudget;
+    p.cache_doubles = (int)((p.smem - vec) / sizeof(double));
+    return p;
+}
+
+struct TrdWork {
+    double *A, *Vt, *Z0, *Z1;          // [group][N][LD]; A doubles as U and X
+    double *tau, *d, *e, *sgn, *D0, *D1, *dsc, *dl, *w, *zh;   // [group][LD]
+    int32_t *nd, *dfl, *rank;          // [group][LD]
+    stedc::Rotation* rot;              // [group][LD]
+    int32_t *kc, *nr;                  // [group][2^L]
+    GemmTask* tasks;                   // [group][2^L]
+    GemmTask* wytasks;                 // [group][nblk]
+    double *Gm, *T;                    // [group][nblk][kWY][kWY]
+    double *Wa, *Wb;                   // [group][N][kWY]
+    double* xch;                       // [ngroups][4][LD]
+    unsigned* flags;                   // [ngroups][G]
+};
+
+void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
+    const size_t g = (size_t)p.group, m = (size_t)N * p.LD, v = (size_t)p.LD;
+    const size_t nodes = (size_t)1 << p.L;
+    w->A = ar.take<double>(g * m);
+    w->Vt = ar.take<double>(g * m);
+    w->Z0 = ar.take<double>(g * m);
+    w->Z1 = ar.take<double>(g * m);
+    w->tau = ar.take<double>(g * v);
+    w->d = ar.take<double>(g * v);
+    w->e = ar.take<double>(g * v);
+    w->sgn = ar.take<double>(g * v);
+    w->D0 = ar.take<double>(g * v);
+    w->D1 = ar.take<double>(g * v);
+    w->dsc = ar.take<double>(g * v);
+    w->dl = ar.take<double>(g * v);
+    w->w = ar.take<double>(g * v);
+    w->zh = ar.take<double>(g * v);
+    w->nd = ar.take<int32_t>(g * v);
+    w->dfl = ar.take<int32_t>(g * v);
+    w->rank = ar.take<int32_t>(g * v);
+    w->rot = ar.take<stedc::Rotation>(g * v);
+    w->kc = ar.take<int32_t>(g * nodes);
+    w->nr = ar.take<int32_t>(g * nodes);
+    w->tasks = ar.take<GemmTask>(g * nodes);
+    w->wytasks = ar.take<GemmTask>(g * p.nblk);
+    w->Gm = ar.take<double>(g * p.nblk * kWY * kWY);
+    w->T = ar.take<double>(g * p.nblk * kWY * kWY);
+    w->Wa = ar.take<double>(g * (size_t)N * kWY);
+    w->Wb = ar.take<double>(g * (size_t)N * kWY);
+    w->xch = ar.take<double>((size_t)p.ngroups * 4 * v);
+    w->flags = ar.take<unsigned>((size_t)p.ngroups * kNumSM);
+}
+
+}  // namespace
+
+bool eig_full_tridiag_supported(int N) {
+    // three vectors of the reduction must fit in shared memory next to at least one cached row
+    const size_t LD = (size_t)((N + 3) & ~3);
+    return N > 256 && sizeof(double) * 4 * LD <= kTrdSmemBudget;
+}
+
+size_t eig_full_tridiag_workspace_bytes(int B, int N) {
+    Arena ar(nullptr, 0);
+    TrdWork w;
+    trd_carve(ar, &w, N, make_plan(B, N));
+    return ar.off + 256;
+}
+
+int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st) {
+    const TrdPlan p = make_plan(B, N);
+    Arena ar(workspace, workspace_bytes);
+    TrdWork w;
+    trd_carve(ar, &w, N, p);
+    if (!ar.ok()) return SCB_ERR_WORKSPACE;
+    const int LD = p.LD, L = p.L;
+    const int64_t mstride = (int64_t)N * LD, vstride = LD;
+    SCB_CUDA(cudaFuncSetAttribute(sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    SCB_CUDA(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * N + 64));
+    const size_t lsmem = sizeof(double) * 2 * kLeaf * (kLeaf + 1);
+    SCB_CUDA(cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    const size_t tsmem = sizeof(double) * kWY * (kWY + 1);
+    SCB_CUDA(cudaFuncSetAttribute(wy_tfactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+
+    for (int s0 = 0; s0 < B; s0 += p.group) {
+        const int live = (B - s0 < p.group) ? B - s0 : p.group;
+        // ---- 1. tridiagonalisation
+        trd_init_kernel<<<dim3((unsigned)ceil_div((int64_t)N * LD, 256), (unsigned)live), 256, 0, st>>>(
+            N, LD, A + (int64_t)s0 * N * N, w.A);
+        SCB_LAUNCH_CHECK();
+        SCB_CUDA(cudaMemsetAsync(w.Vt, 0, sizeof(double) * (size_t)live * mstride, st));
+        SCB_CUDA(cudaMemsetAsync(w.Z0, 0, sizeof(double) * (size_t)live * mstride, st));
+        SCB_CUDA(cudaMemsetAsync(w.Z1, 0, sizeof(double) * (size_t)live * mstride, st));
+        SCB_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * (size_t)p.ngroups * kNumSM, st));
+        TrdParams tp;
+        tp.N = N; tp.LD = LD; tp.B = live; tp.G = p.G;
+        tp.ngroups = p.ngroups < live ? p.ngroups : live;
+        tp.cache_doubles = p.cache_doubles;
+        tp.A = w.A; tp.Vt = w.Vt; tp.tau = w.tau; tp.d = w.d; tp.e = w.e; tp.xch = w.xch; tp.flags = w.flags;
+        void* kargs[] = {&tp};
+        SCB_CUDA(cudaLaunchCooperativeKernel((const void*)sytrd_kernel, dim3((unsigned)(tp.ngroups * tp.G)),
+                                             dim3(kTrdThreads), kargs, p.smem, st));
+        count_launches(1);
+
+        // ---- 2. divide and conquer
+        DcWork W;
+        W.N = N; W.LD = LD; W.L = L;
+        W.d = w.d; W.e = w.e; W.sgn = w.sgn; W.D0 = w.D0; W.D1 = w.D1; W.Z0 = w.Z0; W.Z1 = w.Z1; W.U = w.A;
+        W.dsc = w.dsc; W.dl = w.dl; W.w = w.w; W.zh = w.zh; W.nd = w.nd; W.dfl = w.dfl; W.rot = w.rot;
+        W.kc = w.kc; W.nr = w.nr; W.tasks = w.tasks; W.vstride = vstride; W.mstride = mstride;
+        dc_setup_kernel<<<live, 1024, 0, st>>>(W);
+        SCB_LAUNCH_CHECK();
+        dc_leaf_kernel<<<dim3(1u << L, (unsigned)live), 512, lsmem, st>>>(W);
+        SCB_LAUNCH_CHECK();
+        double *Dcur = w.D0, *Dnew = w.D1, *Zcur = w.Z0, *Znew = w.Z1;
+        for (int level = L - 1; level >= 0; --level) {
+            const unsigned nodes = 1u << level;
+            int lo, hi;
+            node_range(N, level, (int)nodes - 1, &lo, &hi);   // the last node of a level is the largest
+            const int nmax = hi - lo;
+            dc_prepare_kernel<<<dim3(nodes, (unsigned)live), 1024, 20 * (size_t)nmax + 64, st>>>(W, level, Dcur, Zcur, Znew);
+            SCB_LAUNCH_CHECK();
+            dc_rotate_kernel<<<dim3((unsigned)ceil_div(nmax, 256), nodes, (unsigned)live), 256, 0, st>>>(W, level, Zcur);
+            SCB_LAUNCH_CHECK();
+            dc_secular_kernel<<<dim3((unsigned)ceil_div(nmax, 8), nodes, (unsigned)live), 256, 0, st>>>(W, level, Dnew);
+            SCB_LAUNCH_CHECK();
+            dc_zhat_kernel<<<dim3((unsigned)ceil_div(nmax, 32), nodes, (unsigned)live), 1024, 0, st>>>(W, level);
+            SCB_LAUNCH_CHECK();
+            dc_vectors_kernel<<<dim3((unsigned)ceil_div(nmax, 8), nodes, (unsigned)live), 256, 0, st>>>(W, level);
+            SCB_LAUNCH_CHECK();
+            // tasks are stored [matrix][node]: contiguous over the live matrices only if nodes is the stride
+            SCB_TRY((launch_gemm<true, false>(GemmTask{}, w.tasks, nmax, nmax, (int)nodes * live, 0, 0, 0, st)));
+            dc_copy_deflated_kernel<<<dim3((unsigned)nmax, nodes, (unsigned)live), 128, 0, st>>>(W, level, Zcur, Znew, Dnew);
+            SCB_LAUNCH_CHECK();
+            double* td = Dcur; Dcur = Dnew; Dnew = td;
+            double* tz = Zcur; Zcur = Znew; Znew = tz;
+        }
+        dc_rank_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)live), 256, 0, st>>>(
+            N, vstride, Dcur, w.rank, eigval + (int64_t)s0 * N);
+        SCB_LAUNCH_CHECK();
+        double* X = w.A;   // U is dead after the last merge
+        dc_permute_kernel<<<dim3((unsigned)ceil_div(LD, 256), (unsigned)N, (unsigned)live), 256, 0, st>>>(
+            N, LD, vstride, mstride, Zcur, w.rank, w.sgn, X);
+        SCB_LAUNCH_CHECK();
+
+        // ---- 3. back-transformation  X <- X (I - V T V^T) per block, last block first
+        const int nblk = p.nblk;
+        {
+            // Gram matrices of all blocks in one launch (the merge tasks are dead by now)
+            wy_gram_tasks_kernel<<<(unsigned)ceil_div(nblk * live, 128), 128, 0, st>>>(N, LD, nblk, live, mstride, w.Vt, w.Gm,
+                                                                                       w.wytasks);
+            SCB_LAUNCH_CHECK();
+            SCB_TRY((launch_gemm<true, true>(GemmTask{}, w.wytasks, kWY, kWY, nblk * live, 0, 0, 0, st)));
+            wy_tfactor_kernel<<<dim3((unsigned)nblk, (unsigned)live), 256, tsmem, st>>>(N, vstride, nblk, w.tau, w.Gm, w.T);
+            SCB_LAUNCH_CHECK();
+        }
+        for (int b = nblk - 1; b >= 0; --b) {
+            const int j0 = b * kWY;
+            const int nb = (N - 1 - j0 < kWY) ? N - 1 - j0 : kWY;
+            const int i0 = j0 & ~1;   // the reflectors of this block vanish below component j0+1
+            GemmTask g;
+            // Wa[m][a] = sum_i X[m][i] Vt[j0+a][i]
+            g.A = X + i0; g.B = w.Vt + (int64_t)j0 * LD + i0; g.C = w.Wa; g.bidx = nullptr;
+            g.M = N; g.N = nb; g.K = N - i0; g.lda = LD; g.ldb = LD; g.ldc = kWY; g.alpha = 1.0; g.beta = 0.0;
+            SCB_TRY((launch_gemm<true, true>(g, nullptr, N, nb, live, mstride, mstride, (int64_t)N * kWY, st)));
+            // X <- X Q_b^T = X (I - V T^T V^T):  Wb[m][a] = sum_c Wa[m][c] T[a][c]
+            g.A = w.Wa; g.B = w.T + (int64_t)b * kWY * kWY; g.C = w.Wb;
+            g.M = N; g.N = nb; g.K = nb; g.lda = kWY; g.ldb = kWY; g.ldc = kWY; g.alpha = 1.0; g.beta = 0.0;
+            SCB_TRY((launch_gemm<true, true>(g, nullptr, N, nb, live, (int64_t)N * kWY, (int64_t)nblk * kWY * kWY,
+                                            (int64_t)N * kWY, st)));
+            // X[m][i] -= sum_a Wb[m][a] Vt[j0+a][i]
+            g.A = w.Wb; g.B = w.Vt + (int64_t)j0 * LD + i0; g.C = X + i0;
+            g.M = N; g.N = N - i0; g.K = nb; g.lda = kWY; g.ldb = LD; g.ldc = LD; g.alpha = -1.0; g.beta = 1.0;
+            SCB_TRY((launch_gemm<true, false>(g, nullptr, N, N - i0, live, (int64_t)N * kWY, mstride, mstride, st)));
+        }
+        export_rows_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)N, (unsigned)live), 256, 0, st>>>(
+            N, LD, mstride, X, modes + (int64_t)s0 * N * N);
+        SCB_LAUNCH_CHECK();
+    }
+    return SCB_OK;
+}
+
+}  // namespace scb
