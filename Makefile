@@ -1,7 +1,7 @@
 # Builds libscb200.so (sm_100a) in-tree.  `make` here or __graft_entry__.build().
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-O3,-Wall -Xptxas -v
+NVCCFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-O3,-Wall -Xptxas -v
 SRC := $(wildcard springcraft_b200/csrc/*.cu)
 OBJ := $(patsubst springcraft_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := springcraft_b200/lib/libscb200.so

@@ -25,7 +25,7 @@
 //     reflectors: three DMMA GEMMs per block.
 // No host synchronisation anywhere: every data-dependent size (survivors of a
 // deflation, rotations) stays on the device.
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "jacobi.cuh"
 #include "stedc_core.cuh"
@@ -198,7 +198,6 @@ int launch_gemm(const GemmTask& single, const GemmTask* tasks, int maxM, int max
 // ------------------------------------------------------------------------------------------------------------
 // 1. tridiagonalisation
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kTrdThreads = 1024;
 constexpr int kTrdEpoch = 128;   // columns between two re-packings of the shared-memory row cache
 
 struct TrdParams {
@@ -209,46 +208,60 @@ struct TrdParams {
     double* tau;         // [B][LD]
     double* d;           // [B][LD]
     double* e;           // [B][LD]
-    double* xch;         // [ngroups][2][2][LD]  (p, next column) of even / odd steps
-    unsigned* flags;     // [ngroups][G] barrier epochs, zeroed by the caller
+    double* xch;         // [ngroups][kXchCopies][2][2][LD]  (p, next column) of even / odd steps
+    unsigned* flags;     // [ngroups][148][kInboxPad] barrier inboxes, zeroed by the caller
+    long long* dbg;      // optional [grid][4] cycle counters: phase 1, pass, barrier, re-pack (SCB_TRD_DEBUG)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+constexpr int kInboxPad = 160;   // row pitch of the barrier inboxes (>= 148 CTAs, whole 128-byte lines)
+constexpr int kXchCopies = 4;    // replicas of the exchange vectors: 1/4 of the CTAs read each (no hot L2 lines)
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
-// all CTAs of a group: every CTA publishes its epoch, one thread per member CTA waits for that member
-__device__ __forceinline__ void group_barrier(unsigned* flags, int me, int G, unsigned epoch) {
+// All CTAs of a group.  Push model: thread t of CTA `me` writes the epoch into the inbox of CTA t and then polls
+// slot t of its OWN inbox, so every CTA spins on lines nobody else reads (one shared flag line polled by 148 SMs
+// saturates its L2 slice and slows every other access of the step).
+__device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, unsigned epoch) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release_u32(flags + me, epoch);
-    }
     if ((int)threadIdx.x < G) {
-        while (ld_acquire_u32(flags + threadIdx.x) < epoch) {}
+        __threadfence();   // the CTA's writes (ordered before this thread by the barrier) become visible first
+        st_volatile_u32(inbox + (size_t)threadIdx.x * kInboxPad + me, epoch);
+        const unsigned* mine = inbox + (size_t)me * kInboxPad + threadIdx.x;
+        while (ld_volatile_u32(mine) < epoch) {}
+        __threadfence();
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+// (Measured dead end: letting the exchanged values carry their own arrival flag -- every slot armed with a NaN
+// payload and polled by its consumers, no barrier -- is SLOWER than the barrier below: 148 x 1024 threads spinning
+// on shared lines delay the producers' stores; C2 65 ms instead of 51 ms.)
+constexpr int kXchBufs = 2;   // even / odd steps
+
+// sum over the CTA with ONE barrier: `red` must not be reused before another barrier (callers alternate two arrays)
+template <int NT>
+__device__ __forceinline__ double block_sum_nt1(double v, double* red) {
     v = warp_sum(v);
-    __syncthreads();
     if (lane_id() == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kTrdThreads / 32; ++w) t += red[w];
-    return t;
+    return warp_sum(lane_id() < NT / 32 ? red[lane_id()] : 0.0);
 }
 
+constexpr int kTrdMaxRows = 64;   // rows of one CTA (make_plan keeps ceil(N / G) below this)
+constexpr int kTrdMaxSeg = 8;     // column segments a row pair is split into when the CTA has few rows
+
+template <int kTrdThreads>
 __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
     extern __shared__ __align__(16) double tsm[];
-    __shared__ double red[kTrdThreads / 32];
+    __shared__ double redA[32], redB[32], bc[4];
+    __shared__ double partial[kTrdMaxSeg][kTrdMaxRows];
     const int N = P.N, LD = P.LD, G = P.G;
     const int grp = blockIdx.x / G, c = blockIdx.x % G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -256,9 +269,17 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
     double* wprev = tsm + LD;
     double* vcur = tsm + 2 * LD;
     double* cache = tsm + 3 * LD;
-    unsigned* flags = P.flags + (size_t)grp * G;
-    double* xch = P.xch + (size_t)grp * 4 * LD;
+    unsigned* flags = P.flags + (size_t)grp * kNumSM * kInboxPad;
+    const size_t xcopy = (size_t)kXchBufs * 2 * LD;                 // one replica: [step % 2][p | column][LD]
+    double* xch_all = P.xch + (size_t)grp * kXchCopies * xcopy;
+    const double* xch = xch_all + (size_t)(c % kXchCopies) * xcopy;  // the replica this CTA reads
     unsigned epoch = 0;
+#ifdef SCB_TRD_TIMING   // per-phase cycle counters (they cost registers: development builds only)
+    long long t_ph1 = 0, t_pass = 0, t_bar = 0, t_pack = 0, t0 = clock64(), t1;
+#define TRD_LAP(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+#else
+#define TRD_LAP(acc) do { } while (0)
+#endif
     const int nown = (c < N) ? (N - c + G - 1) / G : 0;   // rows c, c+G, ...
 
     for (int s = grp; s < P.B; s += P.ngroups) {
@@ -269,6 +290,8 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
         double* ee = P.e + (size_t)s * LD;
         int cache_col0 = 0, cache_len = LD, cache_rows = 0;
         double tau_prev = 0.0;
+        for (int i = tid; i < 3 * LD; i += kTrdThreads) tsm[i] = 0.0;   // the padding [N, LD) of the vectors stays zero
+        __syncthreads();
 
         for (int j = 0; j < N; ++j) {
             // ---- re-pack the row cache: rows are only needed from column j+1 on
@@ -295,102 +318,171 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 }
                 __syncthreads();
             }
-            // ---- phase 1 (every CTA, redundantly): w_{j-1}, d_j, column j, reflector j
-            double dj;
-            if (j == 0) {
-                for (int i = tid; i < N; i += kTrdThreads) vcur[i] = A[(size_t)i * LD];
-                __syncthreads();
-                dj = vcur[0];
-            } else {
-                const double* pbuf = xch + (size_t)((j - 1) & 1) * 2 * LD;
-                const double* cbuf = pbuf + LD;
+            TRD_LAP(t_pack);
+            // ---- phase 1 (every CTA, redundantly): w_{j-1}, d_j, column j, reflector j.  Thread t owns the
+            //      components j + t, j + t + 1024, ... through all steps, so only the reductions need barriers
+            double dj = 0.0;
+            {
                 double acc = 0.0;
-                for (int i = j + tid; i < N; i += kTrdThreads) {
-                    const double p = __ldcg(pbuf + i);
-                    wprev[i] = p;
-                    acc += p * vprev[i];
+                if (j == 0) {
+                    for (int i = tid; i < N; i += kTrdThreads) vcur[i] = A[(size_t)i * LD];   // column 0
+                } else {
+                    const double* pbuf = xch + (size_t)((j - 1) % kXchBufs) * 2 * LD;
+                    const double* cbuf = pbuf + LD;
+                    for (int i = j + tid; i < N; i += kTrdThreads) {
+                        const double p = __ldcg(pbuf + i), cv = __ldcg(cbuf + i);
+                        wprev[i] = p;
+                        vcur[i] = cv;
+                        acc = fma(p, vprev[i], acc);
+                    }
+                    if (tid == 0) bc[0] = wprev[j];   // p_j
                 }
-                const double dot = block_sum_1024(acc, red);
+                const double dot = block_sum_nt1<kTrdThreads>(acc, redA);
                 const double kappa = 0.5 * tau_prev * dot;
-                for (int i = j + tid; i < N; i += kTrdThreads) wprev[i] -= kappa * vprev[i];
-                __syncthreads();
-                const double wj = wprev[j];
-                dj = __ldcg(cbuf + j) - 2.0 * wj;   // vprev[j] == 1
-                for (int i = j + 1 + tid; i < N; i += kTrdThreads)
-                    vcur[i] = __ldcg(cbuf + i) - (vprev[i] * wj + wprev[i]);
-                __syncthreads();
-            }
-            double tau_cur = 0.0, beta = 0.0;
-            if (j < N - 1) {
-                const double x0 = vcur[j + 1];
-                beta = x0;
-                if (j < N - 2) {
-                    double acc = 0.0;
-                    for (int i = j + 2 + tid; i < N; i += kTrdThreads) acc += vcur[i] * vcur[i];
-                    const double sigma = block_sum_1024(acc, red);
+                const double wj = (j > 0) ? bc[0] - kappa : 0.0;   // vprev[j] == 1
+                double sig = 0.0;
+                if (j > 0) {
+                    for (int i = j + tid; i < N; i += kTrdThreads) {
+                        const double v = vprev[i];
+                        const double w = wprev[i] - kappa * v;
+                        wprev[i] = w;
+                        const double a = vcur[i] - (v * wj + w);   // column j of A_j (for i == j: d_j)
+                        if (i == j) { bc[1] = a; vcur[i] = 0.0; }
+                        else {
+                            vcur[i] = a;
+                            if (i == j + 1) bc[2] = a; else sig = fma(a, a, sig);
+                        }
+                    }
+                } else {
+                    for (int i = tid; i < N; i += kTrdThreads) {
+                        const double a = vcur[i];
+                        if (i == 0) { bc[1] = a; vcur[i] = 0.0; }
+                        else if (i == 1) bc[2] = a;
+                        else sig = fma(a, a, sig);
+                    }
+                }
+                const double sigma = block_sum_nt1<kTrdThreads>(sig, redB);
+                dj = bc[1];
+                double tau_cur = 0.0, beta = 0.0;
+                if (j < N - 1) {
+                    const double x0 = bc[2];
+                    beta = x0;
                     if (sigma > 0.0) {
-                        const double nrm = sqrt(x0 * x0 + sigma);
+                        const double nrm = sqrt(fma(x0, x0, sigma));
                         beta = -copysign(nrm, x0);
                         tau_cur = (beta - x0) / beta;
                         const double scal = 1.0 / (x0 - beta);
-                        for (int i = j + 2 + tid; i < N; i += kTrdThreads) vcur[i] *= scal;
+                        for (int i = j + tid; i < N; i += kTrdThreads)
+                            if (i >= j + 2) vcur[i] *= scal;
                     }
+                    if (tid == 1) vcur[j + 1] = 1.0;   // thread 1 owns component j+1
                 }
                 __syncthreads();
-                if (tid == 0) vcur[j + 1] = 1.0;
-                __syncthreads();
-            }
-            if ((j % G) == c) {
-                if (tid == 0) {
-                    dd[j] = dj;
-                    if (j < N - 1) { ee[j] = beta; tau[j] = tau_cur; }
+                if ((j % G) == c) {
+                    if (tid == 0) {
+                        dd[j] = dj;
+                        if (j < N - 1) { ee[j] = beta; tau[j] = tau_cur; }
+                    }
+                    if (j < N - 1)
+                        for (int i = j + 1 + tid; i < N; i += kTrdThreads) Vt[(size_t)j * LD + i] = vcur[i];
                 }
-                if (j < N - 1)
-                    for (int i = j + 1 + tid; i < N; i += kTrdThreads) Vt[(size_t)j * LD + i] = vcur[i];
-            }
-            if (j == N - 1) break;
-            // ---- pass j: rows i > j of this CTA: apply update j-1, multiply with reflector j
-            {
-                double* pout = xch + (size_t)(j & 1) * 2 * LD;
+                if (j == N - 1) break;
+                TRD_LAP(t_ph1);
+                // ---- pass j: rows i > j of this CTA: apply update j-1, multiply with reflector j.
+                //      Task = (pair of rows, column segment); a lane handles two adjacent columns of both rows.
+                double* pout = xch_all + (size_t)(j % kXchBufs) * 2 * LD;   // replica 0; replica k at + k * xcopy
                 double* cout = pout + LD;
                 const int rmin = (j + 1 > c) ? (j + 1 - c + G - 1) / G : 0;
-                for (int r = rmin + warp; r < nown; r += kTrdThreads / 32) {
-                    const int i = c + G * r;
-                    const int q = nown - 1 - r;
-                    double* rowp = (q < cache_rows) ? cache + (size_t)q * cache_len - cache_col0 : A + (size_t)i * LD;
-                    double acc = 0.0, col1 = 0.0;
-                    if (j > 0) {
-                        const double vi = vprev[i], wi = wprev[i];
-#pragma unroll 4
-                        for (int cc = j + 1 + lane; cc < N; cc += 32) {
-                            const double a = rowp[cc] - (vi * wprev[cc] + wi * vprev[cc]);
-                            rowp[cc] = a;
-                            acc = fma(a, vcur[cc], acc);
-                            if (cc == j + 1) col1 = a;
+                const int na = nown - rmin;                   // rows alive
+                const int npairs = (na + 1) >> 1;
+                int nseg = npairs > 0 ? (kTrdThreads / 32) / npairs : 1;
+                if (nseg < 1) nseg = 1;
+                if (nseg > kTrdMaxSeg) nseg = kTrdMaxSeg;
+                const int cb = (j + 1) & ~1;                  // first column pair (if it starts at column j: vcur[j] == 0)
+                const int nchunk = (LD - cb + 63) >> 6;       // chunks of 64 columns
+                const int cps = (nchunk + nseg - 1) / nseg;
+                for (int task = warp; task < npairs * nseg; task += kTrdThreads / 32) {
+                    const int pr = task / nseg, sg = task - pr * nseg;
+                    const int r0 = rmin + 2 * pr;
+                    const bool two = (r0 + 1 < nown);
+                    const int r1 = two ? r0 + 1 : r0;
+                    const int i0 = c + G * r0, i1 = c + G * r1;
+                    const int q0 = nown - 1 - r0, q1 = nown - 1 - r1;
+                    double* row0 = (q0 < cache_rows) ? cache + (size_t)q0 * cache_len - cache_col0 : A + (size_t)i0 * LD;
+                    double* row1 = (q1 < cache_rows) ? cache + (size_t)q1 * cache_len - cache_col0 : A + (size_t)i1 * LD;
+                    const double v0 = vprev[i0], w0 = wprev[i0], v1 = vprev[i1], w1 = wprev[i1];
+                    double acc0 = 0.0, acc1 = 0.0;
+                    const int ch_end = min(nchunk, (sg + 1) * cps);
+                    for (int ch = sg * cps; ch < ch_end; ch += 2) {
+                        double2 a0[2], a1[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int cc = cb + ((ch + u) << 6) + 2 * lane;
+                            if (ch + u < ch_end && cc < LD) {
+                                a0[u] = *reinterpret_cast<const double2*>(row0 + cc);
+                                a1[u] = *reinterpret_cast<const double2*>(row1 + cc);
+                            }
                         }
-                    } else {
-#pragma unroll 4
-                        for (int cc = 1 + lane; cc < N; cc += 32) {
-                            const double a = rowp[cc];
-                            acc = fma(a, vcur[cc], acc);
-                            if (cc == 1) col1 = a;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int cc = cb + ((ch + u) << 6) + 2 * lane;
+                            if (ch + u < ch_end && cc < LD) {
+                                const double2 vp = *reinterpret_cast<const double2*>(vprev + cc);
+                                const double2 wp = *reinterpret_cast<const double2*>(wprev + cc);
+                                const double2 vc = *reinterpret_cast<const double2*>(vcur + cc);
+                                double2 x = a0[u];
+                                x.x -= (v0 * wp.x + w0 * vp.x);
+                                x.y -= (v0 * wp.y + w0 * vp.y);
+                                *reinterpret_cast<double2*>(row0 + cc) = x;
+                                acc0 = fma(x.x, vc.x, acc0);
+                                acc0 = fma(x.y, vc.y, acc0);
+                                if (cc == cb && sg == 0)                                   // column j+1
+                                    for (int k = 0; k < kXchCopies; ++k) __stcg(cout + k * xcopy + i0, (cb == j) ? x.y : x.x);
+                                if (two) {
+                                    double2 y = a1[u];
+                                    y.x -= (v1 * wp.x + w1 * vp.x);
+                                    y.y -= (v1 * wp.y + w1 * vp.y);
+                                    *reinterpret_cast<double2*>(row1 + cc) = y;
+                                    acc1 = fma(y.x, vc.x, acc1);
+                                    acc1 = fma(y.y, vc.y, acc1);
+                                    if (cc == cb && sg == 0)
+                                        for (int k = 0; k < kXchCopies; ++k) __stcg(cout + k * xcopy + i1, (cb == j) ? y.y : y.x);
+                                }
+                            }
                         }
                     }
-                    acc = warp_sum(acc);
+                    acc0 = warp_sum(acc0);
+                    acc1 = warp_sum(acc1);
                     if (lane == 0) {
-                        __stcg(pout + i, tau_cur * acc);
-                        __stcg(cout + i, col1);
+                        partial[sg][2 * pr] = acc0;
+                        if (two) partial[sg][2 * pr + 1] = acc1;
                     }
                 }
+                __syncthreads();
+                if (tid < na) {
+                    double acc = 0.0;
+                    for (int sg = 0; sg < nseg; ++sg) acc += partial[sg][tid];
+                    const int i = c + G * (rmin + tid);
+                    for (int k = 0; k < kXchCopies; ++k) __stcg(pout + k * xcopy + i, tau_cur * acc);
+                }
+                TRD_LAP(t_pass);
+                ++epoch;
+                group_barrier(flags, c, G, epoch);
+                TRD_LAP(t_bar);
+                double* tmp = vprev; vprev = vcur; vcur = tmp;
+                tau_prev = tau_cur;
             }
-            ++epoch;
-            group_barrier(flags, c, G, epoch);
-            double* tmp = vprev; vprev = vcur; vcur = tmp;
-            tau_prev = tau_cur;
         }
         ++epoch;
         group_barrier(flags, c, G, epoch);   // the exchange buffers are reused by the next matrix of this group
     }
+#ifdef SCB_TRD_TIMING
+    if (P.dbg && tid == 0) {
+        P.dbg[blockIdx.x * 4 + 0] = t_ph1; P.dbg[blockIdx.x * 4 + 1] = t_pass;
+        P.dbg[blockIdx.x * 4 + 2] = t_bar; P.dbg[blockIdx.x * 4 + 3] = t_pack;
+    }
+#endif
+#undef TRD_LAP
 }
 
 // Ap[s][i][j] = symmetric extension of the lower triangle of A[s] (N x N), padded to LD columns with zeros
@@ -830,8 +922,8 @@ struct TrdWork {
     GemmTask* wytasks;                 // [group][nblk]
     double *Gm, *T;                    // [group][nblk][kWY][kWY]
     double *Wa, *Wb;                   // [group][N][kWY]
-    double* xch;                       // [ngroups][4][LD]
-    unsigned* flags;                   // [ngroups][G]
+    double* xch;                       // [ngroups][kXchCopies][2][2][LD]
+    unsigned* flags;                   // [ngroups][148][kInboxPad]
 };
 
 void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
@@ -863,8 +955,8 @@ void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
     w->T = ar.take<double>(g * p.nblk * kWY * kWY);
     w->Wa = ar.take<double>(g * (size_t)N * kWY);
     w->Wb = ar.take<double>(g * (size_t)N * kWY);
-    w->xch = ar.take<double>((size_t)p.ngroups * 4 * v);
-    w->flags = ar.take<unsigned>((size_t)p.ngroups * kNumSM);
+    w->xch = ar.take<double>((size_t)p.ngroups * kXchCopies * kXchBufs * 2 * v);
+    w->flags = ar.take<unsigned>((size_t)p.ngroups * kNumSM * kInboxPad);
 }
 
 }  // namespace
@@ -891,7 +983,13 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
     if (!ar.ok()) return SCB_ERR_WORKSPACE;
     const int LD = p.LD, L = p.L;
     const int64_t mstride = (int64_t)N * LD, vstride = LD;
-    SCB_CUDA(cudaFuncSetAttribute(sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int trd_threads = 512;
+    if (const char* env = getenv("SCB_TRD_THREADS")) trd_threads = atoi(env);
+    const void* trd_fn = (const void*)sytrd_kernel<512>;
+    if (trd_threads == 1024) trd_fn = (const void*)sytrd_kernel<1024>;
+    else if (trd_threads == 256) trd_fn = (const void*)sytrd_kernel<256>;
+    else trd_threads = 512;
+    SCB_CUDA(cudaFuncSetAttribute(trd_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     SCB_CUDA(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * N + 64));
     const size_t lsmem = sizeof(double) * 2 * kLeaf * (kLeaf + 1);
     SCB_CUDA(cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
@@ -907,16 +1005,29 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
         SCB_CUDA(cudaMemsetAsync(w.Vt, 0, sizeof(double) * (size_t)live * mstride, st));
         SCB_CUDA(cudaMemsetAsync(w.Z0, 0, sizeof(double) * (size_t)live * mstride, st));
         SCB_CUDA(cudaMemsetAsync(w.Z1, 0, sizeof(double) * (size_t)live * mstride, st));
-        SCB_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * (size_t)p.ngroups * kNumSM, st));
+        SCB_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * (size_t)p.ngroups * kNumSM * kInboxPad, st));
         TrdParams tp;
         tp.N = N; tp.LD = LD; tp.B = live; tp.G = p.G;
         tp.ngroups = p.ngroups < live ? p.ngroups : live;
         tp.cache_doubles = p.cache_doubles;
         tp.A = w.A; tp.Vt = w.Vt; tp.tau = w.tau; tp.d = w.d; tp.e = w.e; tp.xch = w.xch; tp.flags = w.flags;
+        tp.dbg = nullptr;
+        long long* dbg = nullptr;
+        if (getenv("SCB_TRD_DEBUG")) { cudaMalloc(&dbg, sizeof(long long) * 4 * kNumSM); tp.dbg = dbg; }
         void* kargs[] = {&tp};
-        SCB_CUDA(cudaLaunchCooperativeKernel((const void*)sytrd_kernel, dim3((unsigned)(tp.ngroups * tp.G)),
-                                             dim3(kTrdThreads), kargs, p.smem, st));
+        SCB_CUDA(cudaLaunchCooperativeKernel(trd_fn, dim3((unsigned)(tp.ngroups * tp.G)), dim3((unsigned)trd_threads), kargs,
+                                             p.smem, st));
         count_launches(1);
+        if (dbg) {
+            long long h[4 * kNumSM];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            const int nc = tp.ngroups * tp.G;
+            for (int q = 0; q < nc; q += (nc > 8 ? nc / 8 : 1))
+                fprintf(stderr, "sytrd cta %3d: phase1 %lld pass %lld barrier %lld repack %lld cycles\n", q, h[4 * q], h[4 * q + 1],
+                        h[4 * q + 2], h[4 * q + 3]);
+            cudaFree(dbg);
+        }
 
         // ---- 2. divide and conquer
         DcWork W;
