@@ -271,6 +271,91 @@ def test_eig_full_block_random(N):
     assert np.abs(A @ modes.T - modes.T * lam).max() <= 1e-11 * scale
 
 
+def _check_full(A, lam, modes, tol=1e-12):
+    want = np.linalg.eigvalsh(A)
+    scale = max(np.abs(want).max(), 1e-300)
+    N = len(want)
+    assert np.isfinite(modes).all()
+    assert np.allclose(lam, want, rtol=0, atol=tol * scale)
+    assert np.allclose(modes @ modes.T, np.eye(N), atol=tol)
+    assert np.abs(A @ modes.T - modes.T * lam).max() <= 10 * tol * scale
+
+
+@pytest.mark.parametrize("N", [257, 300, 515, 1001])
+def test_eig_full_tridiag_random(N):
+    """N > 256: Householder tridiagonalisation + divide and conquer + back-transformation (eig_full_tridiag.cu)
+    vs LAPACK (np.linalg.eigh, reference nma.py:61): random symmetric matrices of even and odd order, lower
+    triangle referenced, 1e-13-class eigenvalues, orthogonality and residuals."""
+    import torch
+    from springcraft_b200 import _engine
+    rng = np.random.default_rng(N)
+    A = rng.normal(size=(N, N))
+    A = A + A.T
+    Al = np.tril(A) + 1e3 * np.triu(rng.normal(size=(N, N)), 1)   # garbage in the strict upper triangle
+    lam, modes = _engine.eig_full_dense(torch.from_numpy(Al).cuda())
+    _check_full(A, lam[0].cpu().numpy(), modes[0].cpu().numpy(), tol=2e-13)
+
+
+@pytest.mark.parametrize("kind", ["rank_deficient", "diagonal", "clustered", "decoupled", "toeplitz", "glued", "scaled"])
+def test_eig_full_tridiag_special(kind):
+    """Spectra that stress the deflation and the secular-equation solver of the divide and conquer: many zero
+    eigenvalues, an already diagonal matrix (every reflector is the identity), a tight cluster, two decoupled
+    blocks (zero off-diagonal of the tridiagonal form), the 1-2-1 Toeplitz matrix (deflation by rotation at
+    every level), glued Wilkinson blocks (pairs of eigenvalues agreeing to 1e-9) and a badly scaled matrix."""
+    import torch
+    from springcraft_b200 import _engine
+    N = 420
+    rng = np.random.default_rng(11)
+    A = rng.normal(size=(N, N)); A = A + A.T
+    tol = 2e-13
+    if kind == "rank_deficient":
+        G = rng.normal(size=(N, N - 60)); A = G @ G.T
+    elif kind == "diagonal":
+        A = np.diag(rng.normal(size=N))
+    elif kind == "clustered":
+        A = np.eye(N) + 1e-7 * A
+    elif kind == "decoupled":
+        A[:200, 200:] = 0.0; A[200:, :200] = 0.0
+    elif kind == "toeplitz":
+        A = 2.0 * np.eye(N) - np.eye(N, k=1) - np.eye(N, k=-1)
+    elif kind == "glued":
+        W = np.abs(np.arange(-10, 11)).astype(float)
+        A = np.zeros((N, N))
+        for b in range(N // 21):
+            s = 21 * b
+            A[s:s + 21, s:s + 21] = np.diag(W) + np.eye(21, k=1) + np.eye(21, k=-1)
+            if b: A[s - 1, s] = A[s, s - 1] = 1e-9
+    elif kind == "scaled":
+        sc_ = 10.0 ** rng.uniform(-6, 6, size=N)
+        A = A * np.sqrt(np.outer(sc_, sc_))
+    lam, modes = _engine.eig_full_dense(torch.from_numpy(A.copy()).cuda())
+    _check_full(A, lam[0].cpu().numpy(), modes[0].cpu().numpy(), tol=tol)
+
+
+def test_eig_full_tridiag_batched():
+    """Batches share every launch of the tridiagonal solver: the CTA groups of the reduction work on different
+    matrices concurrently (more matrices than groups, so groups also take several in turn), the merges of all
+    matrices share the launches of a level; matrices with different deflation patterns must each match LAPACK."""
+    import torch
+    from springcraft_b200 import _engine
+    N = 300
+    rng = np.random.default_rng(6)
+    mats = []
+    for kind in range(11):
+        A = rng.normal(size=(N, N)); A = A + A.T
+        if kind % 4 == 1:
+            G = rng.normal(size=(N, N - 40)); A = G @ G.T
+        elif kind % 4 == 2:
+            A = np.diag(rng.normal(size=N))
+        elif kind % 4 == 3:
+            A = np.eye(N) + 1e-6 * A
+        mats.append(A)
+    lam, modes = _engine.eig_full_dense(torch.from_numpy(np.stack(mats)).cuda())
+    lam, modes = lam.cpu().numpy(), modes.cpu().numpy()
+    for A, l, m in zip(mats, lam, modes):
+        _check_full(A, l, m, tol=2e-13)
+
+
 def test_eig_full_block_batched():
     """A batch of matrices shares every launch of the block-Jacobi solver (grid.y = matrix): matrices that
     converge after different numbers of sweeps (random, rank-deficient, already diagonal, tightly clustered)
