@@ -254,7 +254,7 @@ __device__ __forceinline__ double block_sum_nt1(double v, double* red) {
     return warp_sum(lane_id() < NT / 32 ? red[lane_id()] : 0.0);
 }
 
-constexpr int kTrdMaxRows = 64;   // rows of one CTA (make_plan keeps ceil(N / G) below this)
+constexpr int kTrdMaxRows = 128;  // rows of one CTA (make_plan keeps ceil(N / G) below this)
 constexpr int kTrdMaxSeg = 8;     // column segments a row pair is split into when the CTA has few rows
 
 template <int kTrdThreads>
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
 #else
 #define TRD_LAP(acc) do { } while (0)
 #endif
+    constexpr int UNR = (kTrdThreads <= 512) ? 4 : 2;     // chunks in flight per lane (register budget)
     const int nown = (c < N) ? (N - c + G - 1) / G : 0;   // rows c, c+G, ...
 
     for (int s = grp; s < P.B; s += P.ngroups) {
@@ -413,10 +414,10 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                     const double v0 = vprev[i0], w0 = wprev[i0], v1 = vprev[i1], w1 = wprev[i1];
                     double acc0 = 0.0, acc1 = 0.0;
                     const int ch_end = min(nchunk, (sg + 1) * cps);
-                    for (int ch = sg * cps; ch < ch_end; ch += 2) {
-                        double2 a0[2], a1[2];
+                    for (int ch = sg * cps; ch < ch_end; ch += UNR) {
+                        double2 a0[UNR], a1[UNR];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < UNR; ++u) {
                             const int cc = cb + ((ch + u) << 6) + 2 * lane;
                             if (ch + u < ch_end && cc < LD) {
                                 a0[u] = *reinterpret_cast<const double2*>(row0 + cc);
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < UNR; ++u) {
                             const int cc = cb + ((ch + u) << 6) + 2 * lane;
                             if (ch + u < ch_end && cc < LD) {
                                 const double2 vp = *reinterpret_cast<const double2*>(vprev + cc);
@@ -883,7 +884,7 @@ int dc_levels(int N) {
     return L;
 }
 
-constexpr size_t kTrdSmemBudget = 220 * 1024;
+constexpr size_t kTrdSmemBudget = 216 * 1024;   // + 8.5 KB static (partial sums, reduction scratch) <= 227 KB
 
 TrdPlan make_plan(int B, int N) {
     TrdPlan p;
@@ -896,14 +897,23 @@ TrdPlan make_plan(int B, int N) {
     if (g < 1) g = 1;
     if (g > 64) g = 64;
     p.group = (int)(g < (size_t)B ? g : (size_t)B);
-    // CTA groups of the tridiagonalisation: more groups (fewer CTAs per matrix) as long as all rows of a CTA stay in
-    // shared memory; a single matrix always gets every SM
+    // CTA groups of the tridiagonalisation (matrices reduced concurrently).  The per-column cost is dominated by
+    // latencies that do not shrink with the work, so more, smaller groups win as long as the matrices in flight
+    // stay L2-resident (rows that do not fit the shared-memory cache are served from L2): N = 900, 64 matrices:
+    // 4 groups 118 ms, 8 groups 83 ms, 12 groups 79 ms, 16 groups 67..230 ms (L2 thrashing).  A single matrix
+    // always gets every SM.
     p.ngroups = 1;
     const size_t vec = sizeof(double) * 3 * p.LD;
-    for (int ng = 2; ng <= 8 && ng <= p.group; ng *= 2) {
-        const int G = kNumSM / ng;
-        const size_t rows = (size_t)ceil_div(N, G) * p.LD * sizeof(double);
-        if (vec + rows <= kTrdSmemBudget) p.ngroups = ng;
+    {
+        const size_t footprint = sizeof(double) * (size_t)N * p.LD;
+        int ng = (int)(((size_t)56 << 20) / footprint);
+        if (ng > p.group) ng = p.group;
+        while (ng > 1 && (kNumSM / ng < 4 || ceil_div(N, kNumSM / ng) > kTrdMaxRows)) --ng;
+        if (ng >= 1) p.ngroups = ng;
+    }
+    if (const char* env = getenv("SCB_TRD_GROUPS")) {   // A/B switch: CTA groups (matrices reduced concurrently)
+        const int ng = atoi(env);
+        if (ng >= 1 && ng <= 37 && ceil_div(N, kNumSM / ng) <= kTrdMaxRows) p.ngroups = ng < p.group ? ng : p.group;
     }
     p.G = kNumSM / p.ngroups;
     if (p.G > N) p.G = N;
