@@ -46,6 +46,7 @@ struct GemmTask {
     const int32_t* bidx;
     int M, N, K;
     int lda, ldb, ldc;
+    int kmodB;   // > 0: the K index of a K-major B wraps modulo kmodB (B repeated along K: split-K partial sums)
     double alpha, beta;
 };
 
@@ -115,7 +116,8 @@ dgemm_dmma_kernel(GemmTask single, const GemmTask* __restrict__ tasks, int64_t s
                 const int kg = kk + kc;
                 int bytes = 0;
                 if (n0 + r < t.N && kg < t.K) bytes = (kg + 1 < t.K) ? 16 : 8;
-                cp_async16z(&b_s[r * kLDK + kc], bytes ? (const void*)(t.B + (int64_t)(n0 + r) * t.ldb + kg) : (const void*)t.B, bytes);
+                const int kb = t.kmodB > 0 ? kg % t.kmodB : kg;
+                cp_async16z(&b_s[r * kLDK + kc], bytes ? (const void*)(t.B + (int64_t)(n0 + r) * t.ldb + kb) : (const void*)t.B, bytes);
             } else {
                 const int kr = c >> 6, nc = (c & 63) * 2;
                 int bytes = 0;
@@ -243,6 +245,9 @@ __device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, un
 // (Measured dead end: letting the exchanged values carry their own arrival flag -- every slot armed with a NaN
 // payload and polled by its consumers, no barrier -- is SLOWER than the barrier below: 148 x 1024 threads spinning
 // on shared lines delay the producers' stores; C2 65 ms instead of 51 ms.)
+// Also measured and dropped: two co-resident 256-thread CTAs per SM (no gain), and one 16-CTA thread-block cluster
+// per matrix with the exchange pushed through DSMEM and the hardware cluster barrier (64 x N=900: 98 ms against
+// 89 ms; 256 x N=300: 69 ms against 35 ms -- the per-column cost is the CTA's own chain of reductions).
 constexpr int kXchBufs = 2;   // even / odd steps
 
 // sum over the CTA with ONE barrier: `red` must not be reused before another barrier (callers alternate two arrays)
@@ -330,11 +335,24 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 } else {
                     const double* pbuf = xch + (size_t)((j - 1) % kXchBufs) * 2 * LD;
                     const double* cbuf = pbuf + LD;
-                    for (int i = j + tid; i < N; i += kTrdThreads) {
-                        const double p = __ldcg(pbuf + i), cv = __ldcg(cbuf + i);
-                        wprev[i] = p;
-                        vcur[i] = cv;
-                        acc = fma(p, vprev[i], acc);
+                    // all L2 loads of a thread are issued before the first use (one round trip, not one per element)
+                    constexpr int EPT = 8;
+                    for (int base = j + tid; base < N; base += kTrdThreads * EPT) {
+                        double pr[EPT], cr[EPT];
+#pragma unroll
+                        for (int u = 0; u < EPT; ++u) {
+                            const int i = base + u * kTrdThreads;
+                            if (i < N) { pr[u] = __ldcg(pbuf + i); cr[u] = __ldcg(cbuf + i); }
+                        }
+#pragma unroll
+                        for (int u = 0; u < EPT; ++u) {
+                            const int i = base + u * kTrdThreads;
+                            if (i < N) {
+                                wprev[i] = pr[u];
+                                vcur[i] = cr[u];
+                                acc = fma(pr[u], vprev[i], acc);
+                            }
+                        }
                     }
                     if (tid == 0) bc[0] = wprev[j];   // p_j
                 }
@@ -638,6 +656,7 @@ dc_prepare_kernel(DcWork W, int level, const double* __restrict__ Dcur, const do
         g.bidx = nd;
         g.M = k; g.N = n; g.K = k;
         g.lda = LD; g.ldb = LD; g.ldc = LD;
+        g.kmodB = 0;
         g.alpha = 1.0; g.beta = 0.0;
         W.tasks[s * nodes + t] = g;
     }
@@ -854,6 +873,33 @@ __global__ void wy_gram_tasks_kernel(int N, int LD, int nblk, int live, int64_t 
     g.bidx = nullptr;
     g.M = nb; g.N = nb; g.K = N - j0;
     g.lda = LD; g.ldb = LD; g.ldc = kWY;
+    g.kmodB = 0;
+    g.alpha = 1.0; g.beta = 0.0;
+    tasks[q] = g;
+}
+
+// GEMM tasks of  Wa = X V_b  for every block, matrix and K split: Wa[s][m][split * kWY + a]
+__global__ void wy_w_tasks_kernel(int N, int LD, int nblk, int live, int S, int64_t mstride, const double* __restrict__ X,
+                                  const double* __restrict__ Vt, double* __restrict__ Wa, GemmTask* __restrict__ tasks) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nblk * live * S) return;
+    const int b = q / (live * S), s = (q / S) % live, sp = q % S;
+    const int j0 = b * kWY;
+    const int nb = min(kWY, N - 1 - j0);
+    const int K = N - j0;
+    const int Kc = (((K + S - 1) / S) + 15) & ~15;
+    const int k0 = sp * Kc;
+    int Ks = K - k0;
+    if (Ks > Kc) Ks = Kc;
+    if (Ks < 0) Ks = 0;
+    GemmTask g;
+    g.A = X + s * mstride + j0 + (Ks > 0 ? k0 : 0);
+    g.B = Vt + s * mstride + (int64_t)j0 * LD + j0 + (Ks > 0 ? k0 : 0);
+    g.C = Wa + (int64_t)s * N * S * kWY + sp * kWY;
+    g.bidx = nullptr;
+    g.M = N; g.N = nb; g.K = Ks;
+    g.lda = LD; g.ldb = LD; g.ldc = S * kWY;
+    g.kmodB = 0;
     g.alpha = 1.0; g.beta = 0.0;
     tasks[q] = g;
 }
@@ -872,6 +918,7 @@ export_rows_kernel(int N, int LD, int64_t mstride, const double* __restrict__ X,
 // ------------------------------------------------------------------------------------------------------------
 struct TrdPlan {
     int LD, L, G, ngroups, group, nblk, cache_doubles;
+    int wsplit;   // K splits of the skinny product X V_b of the back-transformation
     size_t smem;
 };
 
@@ -917,6 +964,9 @@ TrdPlan make_plan(int B, int N) {
     }
     p.G = kNumSM / p.ngroups;
     if (p.G > N) p.G = N;
+    // X V_b has only N/128 x 1 tiles: split K until the launch fills the GPU
+    p.wsplit = 1;
+    while (p.wsplit < 6 && ceil_div(N, kTM) * p.group * p.wsplit < kNumSM && N / (p.wsplit + 1) >= 256) ++p.wsplit;
     p.smem = kTrdSmemBudget;
     p.cache_doubles = (int)((p.smem - vec) / sizeof(double));
     return p;
@@ -930,8 +980,9 @@ struct TrdWork {
     int32_t *kc, *nr;                  // [group][2^L]
     GemmTask* tasks;                   // [group][2^L]
     GemmTask* wytasks;                 // [group][nblk]
+    GemmTask* wtasks;                  // [nblk][group][wsplit]
     double *Gm, *T;                    // [group][nblk][kWY][kWY]
-    double *Wa, *Wb;                   // [group][N][kWY]
+    double *Wa, *Wb;                   // [group][N][wsplit * kWY] partial products, [group][N][kWY]
     double* xch;                       // [ngroups][kXchCopies][2][2][LD]
     unsigned* flags;                   // [ngroups][148][kInboxPad]
 };
@@ -961,9 +1012,10 @@ void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
     w->nr = ar.take<int32_t>(g * nodes);
     w->tasks = ar.take<GemmTask>(g * nodes);
     w->wytasks = ar.take<GemmTask>(g * p.nblk);
+    w->wtasks = ar.take<GemmTask>(g * p.nblk * p.wsplit);
     w->Gm = ar.take<double>(g * p.nblk * kWY * kWY);
     w->T = ar.take<double>(g * p.nblk * kWY * kWY);
-    w->Wa = ar.take<double>(g * (size_t)N * kWY);
+    w->Wa = ar.take<double>(g * (size_t)N * kWY * p.wsplit);
     w->Wb = ar.take<double>(g * (size_t)N * kWY);
     w->xch = ar.take<double>((size_t)p.ngroups * kXchCopies * kXchBufs * 2 * v);
     w->flags = ar.take<unsigned>((size_t)p.ngroups * kNumSM * kInboxPad);
@@ -1091,24 +1143,30 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
             wy_tfactor_kernel<<<dim3((unsigned)nblk, (unsigned)live), 256, tsmem, st>>>(N, vstride, nblk, w.tau, w.Gm, w.T);
             SCB_LAUNCH_CHECK();
         }
+        const int S = p.wsplit;
+        wy_w_tasks_kernel<<<(unsigned)ceil_div(nblk * live * S, 128), 128, 0, st>>>(N, LD, nblk, live, S, mstride, X, w.Vt, w.Wa,
+                                                                                   w.wtasks);
+        SCB_LAUNCH_CHECK();
+        // columns of Wa beyond the reflectors of a short last block are never written: keep them finite
+        SCB_CUDA(cudaMemsetAsync(w.Wa, 0, sizeof(double) * (size_t)live * N * S * kWY, st));
         for (int b = nblk - 1; b >= 0; --b) {
             const int j0 = b * kWY;
             const int nb = (N - 1 - j0 < kWY) ? N - 1 - j0 : kWY;
-            const int i0 = j0 & ~1;   // the reflectors of this block vanish below component j0+1
             GemmTask g;
-            // Wa[m][a] = sum_i X[m][i] Vt[j0+a][i]
-            g.A = X + i0; g.B = w.Vt + (int64_t)j0 * LD + i0; g.C = w.Wa; g.bidx = nullptr;
-            g.M = N; g.N = nb; g.K = N - i0; g.lda = LD; g.ldb = LD; g.ldc = kWY; g.alpha = 1.0; g.beta = 0.0;
-            SCB_TRY((launch_gemm<true, true>(g, nullptr, N, nb, live, mstride, mstride, (int64_t)N * kWY, st)));
-            // X <- X Q_b^T = X (I - V T^T V^T):  Wb[m][a] = sum_c Wa[m][c] T[a][c]
+            g.bidx = nullptr; g.kmodB = 0;
+            // Wa[m][split][a] = sum over the split's components i of X[m][i] Vt[j0+a][i]
+            SCB_TRY((launch_gemm<true, true>(GemmTask{}, w.wtasks + (size_t)b * live * S, N, nb, live * S, 0, 0, 0, st)));
+            // x^T <- x^T Q_b^T = x^T (I - V T^T V^T):  Wb[m][a] = sum_{split, c} Wa[m][split][c] T[a][c]
             g.A = w.Wa; g.B = w.T + (int64_t)b * kWY * kWY; g.C = w.Wb;
-            g.M = N; g.N = nb; g.K = nb; g.lda = kWY; g.ldb = kWY; g.ldc = kWY; g.alpha = 1.0; g.beta = 0.0;
-            SCB_TRY((launch_gemm<true, true>(g, nullptr, N, nb, live, (int64_t)N * kWY, (int64_t)nblk * kWY * kWY,
+            g.M = N; g.N = nb; g.K = S * kWY; g.lda = S * kWY; g.ldb = kWY; g.ldc = kWY; g.kmodB = kWY;
+            g.alpha = 1.0; g.beta = 0.0;
+            SCB_TRY((launch_gemm<true, true>(g, nullptr, N, nb, live, (int64_t)N * S * kWY, (int64_t)nblk * kWY * kWY,
                                             (int64_t)N * kWY, st)));
             // X[m][i] -= sum_a Wb[m][a] Vt[j0+a][i]
-            g.A = w.Wb; g.B = w.Vt + (int64_t)j0 * LD + i0; g.C = X + i0;
-            g.M = N; g.N = N - i0; g.K = nb; g.lda = kWY; g.ldb = LD; g.ldc = LD; g.alpha = -1.0; g.beta = 1.0;
-            SCB_TRY((launch_gemm<true, false>(g, nullptr, N, N - i0, live, (int64_t)N * kWY, mstride, mstride, st)));
+            g.A = w.Wb; g.B = w.Vt + (int64_t)j0 * LD + j0; g.C = X + j0;
+            g.M = N; g.N = N - j0; g.K = nb; g.lda = kWY; g.ldb = LD; g.ldc = LD; g.kmodB = 0;
+            g.alpha = -1.0; g.beta = 1.0;
+            SCB_TRY((launch_gemm<true, false>(g, nullptr, N, N - j0, live, (int64_t)N * kWY, mstride, mstride, st)));
         }
         export_rows_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)N, (unsigned)live), 256, 0, st>>>(
             N, LD, mstride, X, modes + (int64_t)s0 * N * N);
