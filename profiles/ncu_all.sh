@@ -9,6 +9,7 @@ cap() {  # name regex skip target
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/${TAG}_$1 python profiles/ncu_targets.py $4 > gpurun_out/${TAG}_$1.log 2>&1
   tail -1 gpurun_out/${TAG}_$1.log
 }
+if [ -z "$ONLY_FULL" ]; then
 STEP_PASSES=1 cap filter resident_filter_kernel 0 c3   # first filter launch: all structures, full degree
 STEP_PASSES=1 cap lanczos resident_lanczos_kernel 0 c3
 STEP_PASSES=1 cap build16 resident_build16_kernel 0 c3
@@ -21,4 +22,7 @@ STEP_PASSES=1 cap assemble assemble_rows_kernel 0 c3
 cap dcc gemm_nt_dmma_kernel 1 dcc
 cap slab dense_slab_apply_kernel 1 slab
 cap tf32 dense_slab_tf32_kernel 1 tf32
+fi
+cap sytrd sytrd_kernel 1 full          # the whole tridiagonalisation is ONE launch
+cap dcgemm dgemm_dmma_kernel 84 full  # 79 GEMM launches per call: #84 = top-level merge of the second call (M = N = K ~ 3,000)
 ls -la gpurun_out/${TAG}_*.ncu-rep

@@ -1,6 +1,6 @@
 """One short run that launches every kernel of the hot path at its natural size; the command that
 `ncu --set full -k regex:<kernel>` wraps (profiles/README.md).  Sizes: C3 batch (STEP_CONF structures x 300 residues),
-C5-sized DCC (n = 4,000, m = 200), C4-sized dense slab product (n = 6,000, b = 128)."""
+C5-sized DCC (n = 4,000, m = 200), C4-sized dense slab product (n = 6,000, b = 128), C2 full spectrum (N = 3,000)."""
 import os
 import sys
 from os.path import dirname, realpath
@@ -15,7 +15,7 @@ from springcraft_b200 import _engine
 from springcraft_b200.dense_solver import DenseRowOperator
 from springcraft_b200.ensemble import enm_ensemble_device
 
-what = set(sys.argv[1:]) or {"c3", "dcc", "slab", "tf32"}
+what = set(sys.argv[1:]) or {"c3", "dcc", "slab", "tf32", "full"}
 if "c3" in what:
     B = int(os.environ.get("STEP_CONF", 4096))
     base, coords, seq = make_ensemble(0, B)
@@ -62,3 +62,11 @@ if "tf32" in what:
                                                _lib.stream_ptr()))
     torch.cuda.synchronize()
     print("tf32 filter step", n, b, float(zp.abs().max()))
+if "full" in what:
+    from synthetic_inputs import synthetic_chain
+    anm = sc.ANM(synthetic_chain(1000, seed=0), sc.HinsenForceField())
+    dense = anm._model_device().dense()
+    for _ in range(2):
+        lam, modes = _engine.eig_full_dense(dense.clone())
+    torch.cuda.synchronize()
+    print("full spectrum N", dense.shape[-1], float(lam[0, -1]))
