@@ -931,10 +931,22 @@ int dc_levels(int N) {
     return L;
 }
 
+// SMs the cooperative kernel can count on (B200: 148); never more than the inbox pitch was sized for
+int trd_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n < 1) {
+        cudaGetLastError();
+        return kNumSM;   // no device visible (size queries on a build host)
+    }
+    return n < kNumSM ? n : kNumSM;
+}
+
 constexpr size_t kTrdSmemBudget = 216 * 1024;   // + 8.5 KB static (partial sums, reduction scratch) <= 227 KB
 
 TrdPlan make_plan(int B, int N) {
     TrdPlan p;
+    const int sms = trd_sm_count();
     p.LD = (N + 3) & ~3;
     p.L = dc_levels(N);
     p.nblk = (int)ceil_div(N - 1, kWY);
@@ -955,18 +967,18 @@ TrdPlan make_plan(int B, int N) {
         const size_t footprint = sizeof(double) * (size_t)N * p.LD;
         int ng = (int)(((size_t)56 << 20) / footprint);
         if (ng > p.group) ng = p.group;
-        while (ng > 1 && (kNumSM / ng < 4 || ceil_div(N, kNumSM / ng) > kTrdMaxRows)) --ng;
+        while (ng > 1 && (sms / ng < 4 || ceil_div(N, sms / ng) > kTrdMaxRows)) --ng;
         if (ng >= 1) p.ngroups = ng;
     }
     if (const char* env = getenv("SCB_TRD_GROUPS")) {   // A/B switch: CTA groups (matrices reduced concurrently)
         const int ng = atoi(env);
-        if (ng >= 1 && ng <= 37 && ceil_div(N, kNumSM / ng) <= kTrdMaxRows) p.ngroups = ng < p.group ? ng : p.group;
+        if (ng >= 1 && ng <= 37 && ceil_div(N, sms / ng) <= kTrdMaxRows) p.ngroups = ng < p.group ? ng : p.group;
     }
-    p.G = kNumSM / p.ngroups;
+    p.G = sms / p.ngroups;
     if (p.G > N) p.G = N;
     // X V_b has only N/128 x 1 tiles: split K until the launch fills the GPU
     p.wsplit = 1;
-    while (p.wsplit < 6 && ceil_div(N, kTM) * p.group * p.wsplit < kNumSM && N / (p.wsplit + 1) >= 256) ++p.wsplit;
+    while (p.wsplit < 6 && ceil_div(N, kTM) * p.group * p.wsplit < sms && N / (p.wsplit + 1) >= 256) ++p.wsplit;
     p.smem = kTrdSmemBudget;
     p.cache_doubles = (int)((p.smem - vec) / sizeof(double));
     return p;
@@ -1024,9 +1036,19 @@ void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
 }  // namespace
 
 bool eig_full_tridiag_supported(int N) {
-    // three vectors of the reduction must fit in shared memory next to at least one cached row
+    // three vectors of the reduction must fit in shared memory next to at least one cached row, and the device must
+    // be able to keep one CTA per SM co-resident (cooperative launch); otherwise the block-Jacobi solver is used
     const size_t LD = (size_t)((N + 3) & ~3);
-    return N > 256 && sizeof(double) * 4 * LD <= kTrdSmemBudget;
+    if (N <= 256 || sizeof(double) * 4 * LD > kTrdSmemBudget) return false;
+    int dev = 0, coop = 1, smem = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) coop = 1;
+        if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+            (size_t)smem < kTrdSmemBudget + 9 * 1024)
+            coop = 0;
+    }
+    cudaGetLastError();
+    return coop != 0;
 }
 
 size_t eig_full_tridiag_workspace_bytes(int B, int N) {
