@@ -223,6 +223,11 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
     asm volatile("st.volatile.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -236,8 +241,7 @@ __device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, un
         __threadfence();   // the CTA's writes (ordered before this thread by the barrier) become visible first
         st_volatile_u32(inbox + (size_t)threadIdx.x * kInboxPad + me, epoch);
         const unsigned* mine = inbox + (size_t)me * kInboxPad + threadIdx.x;
-        while (ld_volatile_u32(mine) < epoch) {}
-        __threadfence();
+        while (ld_acquire_u32(mine) < epoch) {}   // acquire: the data loads after the CTA barrier below see the writes
     }
     __syncthreads();
 }
