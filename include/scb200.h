@@ -284,7 +284,11 @@ int scb_rand_block(int64_t total, uint64_t seed, double *X, void *stream);
 
 /* full symmetric eigendecomposition of dense A[B][N][N] (lower triangle is
  * referenced, like LAPACK dsyevd behind np.linalg.eigh): eigval[B][N] ascending,
- * modes[B][N][N] with ROW k = mode k (nma.py:63).  A is destroyed. */
+ * modes[B][N][N] with ROW k = mode k (nma.py:63).  A is destroyed.
+ * N <= 64: Jacobi in shared memory; N <= 256: block Jacobi; larger N: Householder
+ * tridiagonalisation (one persistent cooperative kernel) + divide and conquer +
+ * compact-WY back-transformation on the FP64 tensor cores; no host synchronisation.
+ * Matrices of a batch share every launch. */
 size_t scb_eig_full_workspace_bytes(int B, int N);
 int scb_eig_full(int B, int N, double *A, double *eigval, double *modes,
                  void *workspace, size_t workspace_bytes, void *stream);

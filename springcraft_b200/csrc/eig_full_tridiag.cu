@@ -212,6 +212,7 @@ struct TrdParams {
     double* e;           // [B][LD]
     double* xch;         // [ngroups][kXchCopies][2][2][LD]  (p, next column) of even / odd steps
     unsigned* flags;     // [ngroups][148][kInboxPad] barrier inboxes, zeroed by the caller
+    unsigned* abort_flag;   // set by a barrier that gave up waiting (zeroed by the caller)
     long long* dbg;      // optional [grid][4] cycle counters: phase 1, pass, barrier, re-pack (SCB_TRD_DEBUG)
 };
 
@@ -235,13 +236,22 @@ __device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
 // All CTAs of a group.  Push model: thread t of CTA `me` writes the epoch into the inbox of CTA t and then polls
 // slot t of its OWN inbox, so every CTA spins on lines nobody else reads (one shared flag line polled by 148 SMs
 // saturates its L2 slice and slows every other access of the step).
-__device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, unsigned epoch) {
+__device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, unsigned epoch, unsigned* abort_flag) {
     __syncthreads();
     if ((int)threadIdx.x < G) {
         __threadfence();   // the CTA's writes (ordered before this thread by the barrier) become visible first
         st_volatile_u32(inbox + (size_t)threadIdx.x * kInboxPad + me, epoch);
         const unsigned* mine = inbox + (size_t)me * kInboxPad + threadIdx.x;
-        while (ld_acquire_u32(mine) < epoch) {}   // acquire: the data loads after the CTA barrier below see the writes
+        // acquire: the data loads after the CTA barrier below see the writes.  A member that never arrives (it can
+        // only be a fault elsewhere) must not hang the device: after ~10 s of spinning the wait is abandoned, every
+        // later barrier of the launch falls through and the host reports SCB_ERR_CUDA.
+        unsigned spins = 0;
+        while (ld_acquire_u32(mine) < epoch) {
+            if ((++spins & 0xFFu) == 0) {
+                if (ld_volatile_u32(abort_flag) != 0) break;
+                if (spins > (1u << 24)) { st_volatile_u32(abort_flag, 1u); break; }
+            }
+        }
     }
     __syncthreads();
 }
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                     const double* pbuf = xch + (size_t)((j - 1) % kXchBufs) * 2 * LD;
                     const double* cbuf = pbuf + LD;
                     // all L2 loads of a thread are issued before the first use (one round trip, not one per element)
-                    constexpr int EPT = 8;
+                    constexpr int EPT = 4;
                     for (int base = j + tid; base < N; base += kTrdThreads * EPT) {
                         double pr[EPT], cr[EPT];
 #pragma unroll
@@ -490,14 +500,14 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 }
                 TRD_LAP(t_pass);
                 ++epoch;
-                group_barrier(flags, c, G, epoch);
+                group_barrier(flags, c, G, epoch, P.abort_flag);
                 TRD_LAP(t_bar);
                 double* tmp = vprev; vprev = vcur; vcur = tmp;
                 tau_prev = tau_cur;
             }
         }
         ++epoch;
-        group_barrier(flags, c, G, epoch);   // the exchange buffers are reused by the next matrix of this group
+        group_barrier(flags, c, G, epoch, P.abort_flag);   // the exchange buffers are reused by the next matrix of this group
     }
 #ifdef SCB_TRD_TIMING
     if (P.dbg && tid == 0) {
@@ -1034,7 +1044,7 @@ void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
     w->Wa = ar.take<double>(g * (size_t)N * kWY * p.wsplit);
     w->Wb = ar.take<double>(g * (size_t)N * kWY);
     w->xch = ar.take<double>((size_t)p.ngroups * kXchCopies * kXchBufs * 2 * v);
-    w->flags = ar.take<unsigned>((size_t)p.ngroups * kNumSM * kInboxPad);
+    w->flags = ar.take<unsigned>((size_t)p.ngroups * kNumSM * kInboxPad + 64);   // + the abort word
 }
 
 }  // namespace
@@ -1093,12 +1103,13 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
         SCB_CUDA(cudaMemsetAsync(w.Vt, 0, sizeof(double) * (size_t)live * mstride, st));
         SCB_CUDA(cudaMemsetAsync(w.Z0, 0, sizeof(double) * (size_t)live * mstride, st));
         SCB_CUDA(cudaMemsetAsync(w.Z1, 0, sizeof(double) * (size_t)live * mstride, st));
-        SCB_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * (size_t)p.ngroups * kNumSM * kInboxPad, st));
+        SCB_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * ((size_t)p.ngroups * kNumSM * kInboxPad + 64), st));
         TrdParams tp;
         tp.N = N; tp.LD = LD; tp.B = live; tp.G = p.G;
         tp.ngroups = p.ngroups < live ? p.ngroups : live;
         tp.cache_doubles = p.cache_doubles;
         tp.A = w.A; tp.Vt = w.Vt; tp.tau = w.tau; tp.d = w.d; tp.e = w.e; tp.xch = w.xch; tp.flags = w.flags;
+        tp.abort_flag = w.flags + (size_t)p.ngroups * kNumSM * kInboxPad;
         tp.dbg = nullptr;
         long long* dbg = nullptr;
         if (getenv("SCB_TRD_DEBUG")) { cudaMalloc(&dbg, sizeof(long long) * 4 * kNumSM); tp.dbg = dbg; }
@@ -1197,6 +1208,15 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
         export_rows_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)N, (unsigned)live), 256, 0, st>>>(
             N, LD, mstride, X, modes + (int64_t)s0 * N * N);
         SCB_LAUNCH_CHECK();
+        // the only host synchronisation of the solver: did a barrier of the cooperative kernel give up?
+        unsigned aborted = 0;
+        SCB_CUDA(cudaMemcpyAsync(&aborted, w.flags + (size_t)p.ngroups * kNumSM * kInboxPad, sizeof(unsigned),
+                                 cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        if (aborted) {
+            set_last_cuda_error(cudaErrorLaunchTimeout, __FILE__, __LINE__);
+            return SCB_ERR_CUDA;
+        }
     }
     return SCB_OK;
 }

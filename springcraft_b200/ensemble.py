@@ -118,7 +118,7 @@ def enm_ensemble(coords, force_field, k=20, kind="anm", masses=None, tol=3e-9, r
 
 def _ensemble_all_modes(coords, force_field, D, masses, return_modes, keep=None):
     """All non-trivial modes per conformation (or the `keep` lowest of them): batched assembly -> dense ->
-    block-Jacobi groups -> MSF."""
+    batched full-spectrum solver (scb_eig_full) -> MSF."""
     from . import _engine
     B, n = int(coords.shape[0]), int(coords.shape[1])
     N = D * n
