@@ -1053,7 +1053,8 @@ bool eig_full_tridiag_supported(int N) {
     // three vectors of the reduction must fit in shared memory next to at least one cached row, and the device must
     // be able to keep one CTA per SM co-resident (cooperative launch); otherwise the block-Jacobi solver is used
     const size_t LD = (size_t)((N + 3) & ~3);
-    if (N <= 256 || sizeof(double) * 4 * LD > kTrdSmemBudget) return false;
+    // (N <= 9,200: the three vectors alone fill the shared memory, rows are then cached only once they have shrunk)
+    if (N <= 256 || sizeof(double) * 3 * LD + 2048 > kTrdSmemBudget) return false;
     int dev = 0, coop = 1, smem = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) coop = 1;
