@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
     unsigned* flags = P.flags + (size_t)grp * kNumSM * kInboxPad;
     const size_t xcopy = (size_t)kXchBufs * 2 * LD;                 // one replica: [step % 2][p | column][LD]
     double* xch_all = P.xch + (size_t)grp * kXchCopies * xcopy;
-    const double* xch = xch_all + (size_t)(c % kXchCopies) * xcopy;  // the replica this CTA reads
+    const int ncopies = G > 80 ? kXchCopies : (G > 40 ? 2 : 1);      // ~37 readers per replica
+    const double* xch = xch_all + (size_t)(c % ncopies) * xcopy;     // the replica this CTA reads
     unsigned epoch = 0;
 #ifdef SCB_TRD_TIMING   // per-phase cycle counters (they cost registers: development builds only)
     long long t_ph1 = 0, t_pass = 0, t_bar = 0, t_pack = 0, t0 = clock64(), t1;
@@ -428,11 +429,21 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 const int rmin = (j + 1 > c) ? (j + 1 - c + G - 1) / G : 0;
                 const int na = nown - rmin;                   // rows alive
                 const int npairs = (na + 1) >> 1;
-                int nseg = npairs > 0 ? (kTrdThreads / 32) / npairs : 1;
-                if (nseg < 1) nseg = 1;
-                if (nseg > kTrdMaxSeg) nseg = kTrdMaxSeg;
                 const int cb = (j + 1) & ~1;                  // first column pair (if it starts at column j: vcur[j] == 0)
                 const int nchunk = (LD - cb + 63) >> 6;       // chunks of 64 columns
+                // column segments per row pair: minimise (rounds of the warps) x (segment length); a segment keeps
+                // at least one full set of chunks in flight (11 pairs on 16 warps: 4 segments = 3 rounds of 1/4)
+                int nseg = 1;
+                {
+                    constexpr int nw = kTrdThreads / 32;
+                    int best = 1 << 30;
+                    for (int sgc = 1; sgc <= kTrdMaxSeg && npairs > 0; ++sgc) {
+                        const int len = (nchunk + sgc - 1) / sgc;
+                        if (sgc > 1 && len < UNR) break;
+                        const int cost = ((npairs * sgc + nw - 1) / nw) * ((len + UNR - 1) / UNR);
+                        if (cost < best) { best = cost; nseg = sgc; }
+                    }
+                }
                 const int cps = (nchunk + nseg - 1) / nseg;
                 for (int task = warp; task < npairs * nseg; task += kTrdThreads / 32) {
                     const int pr = task / nseg, sg = task - pr * nseg;
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                                 acc0 = fma(x.x, vc.x, acc0);
                                 acc0 = fma(x.y, vc.y, acc0);
                                 if (cc == cb && sg == 0)                                   // column j+1
-                                    for (int k = 0; k < kXchCopies; ++k) __stcg(cout + k * xcopy + i0, (cb == j) ? x.y : x.x);
+                                    for (int k = 0; k < ncopies; ++k) __stcg(cout + k * xcopy + i0, (cb == j) ? x.y : x.x);
                                 if (two) {
                                     double2 y = a1[u];
                                     y.x -= (v1 * wp.x + w1 * vp.x);
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                                     acc1 = fma(y.x, vc.x, acc1);
                                     acc1 = fma(y.y, vc.y, acc1);
                                     if (cc == cb && sg == 0)
-                                        for (int k = 0; k < kXchCopies; ++k) __stcg(cout + k * xcopy + i1, (cb == j) ? y.y : y.x);
+                                        for (int k = 0; k < ncopies; ++k) __stcg(cout + k * xcopy + i1, (cb == j) ? y.y : y.x);
                                 }
                             }
                         }
@@ -496,7 +507,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                     double acc = 0.0;
                     for (int sg = 0; sg < nseg; ++sg) acc += partial[sg][tid];
                     const int i = c + G * (rmin + tid);
-                    for (int k = 0; k < kXchCopies; ++k) __stcg(pout + k * xcopy + i, tau_cur * acc);
+                    for (int k = 0; k < ncopies; ++k) __stcg(pout + k * xcopy + i, tau_cur * acc);
                 }
                 TRD_LAP(t_pass);
                 ++epoch;
