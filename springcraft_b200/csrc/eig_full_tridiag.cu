@@ -854,7 +854,7 @@ constexpr int kWY = 128;   // reflectors per compact-WY block
 // T of the block  H_j0 ... H_j0+nb-1 = I - V T V^T  (forward, columnwise): T[a][a] = tau_a,
 // T[0:a, a] = -tau_a T[0:a, 0:a] (V^T v_a)[0:a].  One CTA per block; Gm = V^T V of the block.
 __global__ void __launch_bounds__(256)
-wy_tfactor_kernel(int N, int64_t vstride, int nblk, const double* __restrict__ tau, const double* __restrict__ Gm,
+wy_tfactor_kernel(int N, int64_t vstride, int nblk, int S, const double* __restrict__ tau, double* __restrict__ Gm,
                   double* __restrict__ T) {
     extern __shared__ __align__(16) double wsm[];   // T [kWY][kWY+1]
     constexpr int LDT = kWY + 1;
@@ -862,7 +862,12 @@ wy_tfactor_kernel(int N, int64_t vstride, int nblk, const double* __restrict__ t
     const int s = blockIdx.y, b = blockIdx.x;
     const int j0 = b * kWY;
     const int nb = min(kWY, (N - 1) - j0);   // reflectors j0 .. j0+nb-1 (there are N-1, the last has tau = 0)
-    const double* G = Gm + ((int64_t)s * nblk + b) * kWY * kWY;
+    double* G = Gm + ((int64_t)s * nblk + b) * S * kWY * kWY;   // S split-K partials, summed into the first
+    for (int q = threadIdx.x; q < kWY * kWY; q += blockDim.x) {
+        double acc = G[q];
+        for (int sp = 1; sp < S; ++sp) acc += G[(int64_t)sp * kWY * kWY + q];
+        G[q] = acc;
+    }
     double* Tg = T + ((int64_t)s * nblk + b) * kWY * kWY;
     const double* tv = tau + s * vstride + j0;
     for (int q = threadIdx.x; q < kWY * LDT; q += blockDim.x) wsm[q] = 0.0;
@@ -884,28 +889,68 @@ wy_tfactor_kernel(int N, int64_t vstride, int nblk, const double* __restrict__ t
 }
 
 // GEMM tasks of the Gram matrices Gm[b] = V_b V_b^T of all blocks and matrices
-__global__ void wy_gram_tasks_kernel(int N, int LD, int nblk, int live, int64_t mstride, const double* __restrict__ Vt,
-                                     double* __restrict__ Gm, GemmTask* __restrict__ tasks) {
+__global__ void wy_gram_tasks_kernel(int N, int LD, int nblk, int live, int S, int64_t mstride,
+                                     const double* __restrict__ Vt, double* __restrict__ Gm, GemmTask* __restrict__ tasks) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nblk * live) return;
-    const int s = q / nblk, b = q % nblk;
+    if (q >= nblk * live * S) return;
+    const int sb = q / S, sp = q % S;
+    const int s = sb / nblk, b = sb % nblk;
     const int j0 = b * kWY;
     const int nb = min(kWY, N - 1 - j0);
+    const int K = N - j0;
+    const int Kc = (((K + S - 1) / S) + 15) & ~15;
+    const int k0 = sp * Kc;
+    int Ks = K - k0;
+    if (Ks > Kc) Ks = Kc;
+    if (Ks < 0) Ks = 0;
     GemmTask g;
-    g.A = Vt + s * mstride + (int64_t)j0 * LD + j0;   // the reflectors of this block vanish below component j0+1
+    g.A = Vt + s * mstride + (int64_t)j0 * LD + j0 + (Ks > 0 ? k0 : 0);   // the reflectors vanish below component j0+1
     g.B = g.A;
     g.C = Gm + (int64_t)q * kWY * kWY;
     g.bidx = nullptr;
-    g.M = nb; g.N = nb; g.K = N - j0;
+    g.M = nb; g.N = nb; g.K = Ks;
     g.lda = LD; g.ldb = LD; g.ldc = kWY;
     g.kmodB = 0;
     g.alpha = 1.0; g.beta = 0.0;
     tasks[q] = g;
 }
 
+// GEMM tasks of  VT_b = T_b V_b^T  (rows a of block b: sum_c T[a][c] Vt[j0+c][:]) for every block and matrix
+__global__ void wy_vt_tasks_kernel(int N, int LD, int nblk, int live, int64_t mstride, const double* __restrict__ T,
+                                   const double* __restrict__ Vt, double* __restrict__ VTt, GemmTask* __restrict__ tasks) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nblk * live) return;
+    const int s = q / nblk, b = q % nblk;
+    const int j0 = b * kWY;
+    const int nb = min(kWY, N - 1 - j0);
+    GemmTask g;
+    g.A = T + (int64_t)q * kWY * kWY;
+    g.B = Vt + s * mstride + (int64_t)j0 * LD + j0;
+    g.C = VTt + s * mstride + (int64_t)j0 * LD + j0;
+    g.bidx = nullptr;
+    g.M = nb; g.N = N - j0; g.K = nb;
+    g.lda = kWY; g.ldb = LD; g.ldc = LD;
+    g.kmodB = 0;
+    g.alpha = 1.0; g.beta = 0.0;
+    tasks[q] = g;
+}
+
+// Wb[m][a] = sum over the K splits of Wa[m][split][a]
+__global__ void __launch_bounds__(256)
+wy_reduce_kernel(int N, int S, const double* __restrict__ Wa, double* __restrict__ Wb) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)N * kWY) return;
+    const int m = (int)(q / kWY), a = (int)(q % kWY);
+    const double* src = Wa + (int64_t)blockIdx.y * N * S * kWY + (int64_t)m * S * kWY + a;
+    double acc = 0.0;
+    for (int sp = 0; sp < S; ++sp) acc += src[sp * kWY];
+    Wb[(int64_t)blockIdx.y * N * kWY + q] = acc;
+}
+
 // GEMM tasks of  Wa = X V_b  for every block, matrix and K split: Wa[s][m][split * kWY + a]
 __global__ void wy_w_tasks_kernel(int N, int LD, int nblk, int live, int S, int64_t mstride, const double* __restrict__ X,
-                                  const double* __restrict__ Vt, double* __restrict__ Wa, GemmTask* __restrict__ tasks) {
+                                  const double* __restrict__ Vt, double* __restrict__ Wa, double* __restrict__ Wb,
+                                  GemmTask* __restrict__ tasks) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nblk * live * S) return;
     const int b = q / (live * S), s = (q / S) % live, sp = q % S;
@@ -920,7 +965,7 @@ __global__ void wy_w_tasks_kernel(int N, int LD, int nblk, int live, int S, int6
     GemmTask g;
     g.A = X + s * mstride + j0 + (Ks > 0 ? k0 : 0);
     g.B = Vt + s * mstride + (int64_t)j0 * LD + j0 + (Ks > 0 ? k0 : 0);
-    g.C = Wa + (int64_t)s * N * S * kWY + sp * kWY;
+    g.C = S > 1 ? Wa + (int64_t)s * N * S * kWY + sp * kWY : Wb + (int64_t)s * N * kWY;   // one split: no reduction
     g.bidx = nullptr;
     g.M = N; g.N = nb; g.K = Ks;
     g.lda = LD; g.ldb = LD; g.ldc = S * kWY;
@@ -1018,7 +1063,7 @@ struct TrdWork {
     GemmTask* tasks;                   // [group][2^L]
     GemmTask* wytasks;                 // [group][nblk]
     GemmTask* wtasks;                  // [nblk][group][wsplit]
-    double *Gm, *T;                    // [group][nblk][kWY][kWY]
+    double *Gm, *T;                    // [group][nblk][wsplit][kWY][kWY] partial Gram matrices, [group][nblk][kWY][kWY]
     double *Wa, *Wb;                   // [group][N][wsplit * kWY] partial products, [group][N][kWY]
     double* xch;                       // [ngroups][kXchCopies][2][2][LD]
     unsigned* flags;                   // [ngroups][148][kInboxPad]
@@ -1048,9 +1093,9 @@ void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
     w->kc = ar.take<int32_t>(g * nodes);
     w->nr = ar.take<int32_t>(g * nodes);
     w->tasks = ar.take<GemmTask>(g * nodes);
-    w->wytasks = ar.take<GemmTask>(g * p.nblk);
+    w->wytasks = ar.take<GemmTask>(g * p.nblk * p.wsplit);
     w->wtasks = ar.take<GemmTask>(g * p.nblk * p.wsplit);
-    w->Gm = ar.take<double>(g * p.nblk * kWY * kWY);
+    w->Gm = ar.take<double>(g * p.nblk * kWY * kWY * p.wsplit);
     w->T = ar.take<double>(g * p.nblk * kWY * kWY);
     w->Wa = ar.take<double>(g * (size_t)N * kWY * p.wsplit);
     w->Wb = ar.take<double>(g * (size_t)N * kWY);
@@ -1181,39 +1226,40 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
             N, LD, vstride, mstride, Zcur, w.rank, w.sgn, X);
         SCB_LAUNCH_CHECK();
 
-        // ---- 3. back-transformation  X <- X (I - V T V^T) per block, last block first
+        // ---- 3. back-transformation  x^T <- x^T Q_b^T = x^T (I - V_b T_b^T V_b^T) per block, last block first
         const int nblk = p.nblk;
-        {
-            // Gram matrices of all blocks in one launch (the merge tasks are dead by now)
-            wy_gram_tasks_kernel<<<(unsigned)ceil_div(nblk * live, 128), 128, 0, st>>>(N, LD, nblk, live, mstride, w.Vt, w.Gm,
-                                                                                       w.wytasks);
-            SCB_LAUNCH_CHECK();
-            SCB_TRY((launch_gemm<true, true>(GemmTask{}, w.wytasks, kWY, kWY, nblk * live, 0, 0, 0, st)));
-            wy_tfactor_kernel<<<dim3((unsigned)nblk, (unsigned)live), 256, tsmem, st>>>(N, vstride, nblk, w.tau, w.Gm, w.T);
-            SCB_LAUNCH_CHECK();
-        }
         const int S = p.wsplit;
-        wy_w_tasks_kernel<<<(unsigned)ceil_div(nblk * live * S, 128), 128, 0, st>>>(N, LD, nblk, live, S, mstride, X, w.Vt, w.Wa,
-                                                                                   w.wtasks);
+        double* VTt = Znew;   // both eigenvector buffers of the divide and conquer are dead: rows of  T_b V_b^T
+        {
+            // Gram matrices of all blocks (split along K) in one launch, T factors, then  VT_b = T_b V_b^T  in one launch
+            wy_gram_tasks_kernel<<<(unsigned)ceil_div(nblk * live * S, 128), 128, 0, st>>>(N, LD, nblk, live, S, mstride, w.Vt,
+                                                                                           w.Gm, w.wytasks);
+            SCB_LAUNCH_CHECK();
+            SCB_TRY((launch_gemm<true, true>(GemmTask{}, w.wytasks, kWY, kWY, nblk * live * S, 0, 0, 0, st)));
+            wy_tfactor_kernel<<<dim3((unsigned)nblk, (unsigned)live), 256, tsmem, st>>>(N, vstride, nblk, S, w.tau, w.Gm, w.T);
+            SCB_LAUNCH_CHECK();
+            wy_vt_tasks_kernel<<<(unsigned)ceil_div(nblk * live, 128), 128, 0, st>>>(N, LD, nblk, live, mstride, w.T, w.Vt, VTt,
+                                                                                     w.wytasks);
+            SCB_LAUNCH_CHECK();
+            SCB_TRY((launch_gemm<true, false>(GemmTask{}, w.wytasks, kWY, N, nblk * live, 0, 0, 0, st)));
+        }
+        wy_w_tasks_kernel<<<(unsigned)ceil_div(nblk * live * S, 128), 128, 0, st>>>(N, LD, nblk, live, S, mstride, X, VTt, w.Wa,
+                                                                                   w.Wb, w.wtasks);
         SCB_LAUNCH_CHECK();
-        // columns of Wa beyond the reflectors of a short last block are never written: keep them finite
-        SCB_CUDA(cudaMemsetAsync(w.Wa, 0, sizeof(double) * (size_t)live * N * S * kWY, st));
         for (int b = nblk - 1; b >= 0; --b) {
             const int j0 = b * kWY;
             const int nb = (N - 1 - j0 < kWY) ? N - 1 - j0 : kWY;
+            // Wa[m][split][a] = sum over the split's components i of X[m][i] (T_b V_b^T)[a][i]
+            SCB_TRY((launch_gemm<true, true>(GemmTask{}, w.wtasks + (size_t)b * live * S, N, nb, live * S, 0, 0, 0, st)));
+            if (S > 1) {
+                wy_reduce_kernel<<<dim3((unsigned)ceil_div((int64_t)N * kWY, 256), (unsigned)live), 256, 0, st>>>(N, S, w.Wa, w.Wb);
+                SCB_LAUNCH_CHECK();
+            }
+            // X[m][i] -= sum_a Wb[m][a] Vt[j0+a][i]
             GemmTask g;
             g.bidx = nullptr; g.kmodB = 0;
-            // Wa[m][split][a] = sum over the split's components i of X[m][i] Vt[j0+a][i]
-            SCB_TRY((launch_gemm<true, true>(GemmTask{}, w.wtasks + (size_t)b * live * S, N, nb, live * S, 0, 0, 0, st)));
-            // x^T <- x^T Q_b^T = x^T (I - V T^T V^T):  Wb[m][a] = sum_{split, c} Wa[m][split][c] T[a][c]
-            g.A = w.Wa; g.B = w.T + (int64_t)b * kWY * kWY; g.C = w.Wb;
-            g.M = N; g.N = nb; g.K = S * kWY; g.lda = S * kWY; g.ldb = kWY; g.ldc = kWY; g.kmodB = kWY;
-            g.alpha = 1.0; g.beta = 0.0;
-            SCB_TRY((launch_gemm<true, true>(g, nullptr, N, nb, live, (int64_t)N * S * kWY, (int64_t)nblk * kWY * kWY,
-                                            (int64_t)N * kWY, st)));
-            // X[m][i] -= sum_a Wb[m][a] Vt[j0+a][i]
             g.A = w.Wb; g.B = w.Vt + (int64_t)j0 * LD + j0; g.C = X + j0;
-            g.M = N; g.N = N - j0; g.K = nb; g.lda = kWY; g.ldb = LD; g.ldc = LD; g.kmodB = 0;
+            g.M = N; g.N = N - j0; g.K = nb; g.lda = kWY; g.ldb = LD; g.ldc = LD;
             g.alpha = -1.0; g.beta = 1.0;
             SCB_TRY((launch_gemm<true, false>(g, nullptr, N, N - j0, live, (int64_t)N * kWY, mstride, mstride, st)));
         }
