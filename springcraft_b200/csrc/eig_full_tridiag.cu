@@ -58,6 +58,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// 8-byte variant for operands whose origin is only 8-byte aligned (odd column offset)
+__device__ __forceinline__ void cp_async8z(void* smem, const void* gmem, int bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
 // copies `bytes` (0, 8 or 16) and zero-fills the rest of the 16-byte chunk
 __device__ __forceinline__ void cp_async16z(void* smem, const void* gmem, int bytes) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -93,6 +99,7 @@ dgemm_dmma_kernel(GemmTask single, const GemmTask* __restrict__ tasks, int64_t s
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    const bool a_odd = AK && ((reinterpret_cast<uintptr_t>(t.A) & 15) != 0);
     auto load_stage = [&](int stage, int kk) {
         double* a_s = sA + stage * kTileDoubles;
         double* b_s = sB + stage * kTileDoubles;
@@ -104,7 +111,13 @@ dgemm_dmma_kernel(GemmTask single, const GemmTask* __restrict__ tasks, int64_t s
                 const int kg = kk + kc;
                 int bytes = 0;
                 if (m0 + r < t.M && kg < t.K) bytes = (kg + 1 < t.K) ? 16 : 8;
-                cp_async16z(&a_s[r * kLDK + kc], bytes ? (const void*)(t.A + (int64_t)(m0 + r) * t.lda + kg) : (const void*)t.A, bytes);
+                const double* src = bytes ? t.A + (int64_t)(m0 + r) * t.lda + kg : t.A;
+                if (a_odd) {   // origin at an odd column: two 8-byte copies
+                    cp_async8z(&a_s[r * kLDK + kc], src, bytes ? 8 : 0);
+                    cp_async8z(&a_s[r * kLDK + kc + 1], bytes == 16 ? src + 1 : t.A, bytes == 16 ? 8 : 0);
+                } else {
+                    cp_async16z(&a_s[r * kLDK + kc], src, bytes);
+                }
             } else {
                 const int kr = c >> 6, mc = (c & 63) * 2;
                 int bytes = 0;
@@ -568,6 +581,7 @@ struct DcWork {           // per matrix (index s) unless noted; vectors have LD 
     double* U;            // [N][LD] differences d_i - lambda_j, then the eigenvectors of the rank-one problems
     double *dsc, *dl, *w, *zh;
     int32_t *nd, *dfl;    // survivors / deflated entries (local indices) per range
+    int32_t *pos, *ndg;   // column of survivor t in the grouped eigenvector matrix; rows gathered in grouped order
     stedc::Rotation* rot;
     int32_t *kc, *nr;     // [B][nodes of the level] survivors and rotations of each merge
     GemmTask* tasks;      // [B * nodes]
@@ -649,12 +663,15 @@ dc_prepare_kernel(DcWork W, int level, const double* __restrict__ Dcur, const do
     double* dd = psm;                      // [n]
     double* z = psm + n;                   // [n]
     int* order = reinterpret_cast<int*>(psm + 2 * n);   // [n]
+    unsigned char* mixed = reinterpret_cast<unsigned char*>(order + n);   // [n]
+    const int n1 = mid - lo;
     const double* D = Dcur + s * W.vstride;
     const double* Z = Zcur + s * W.mstride;
     const double rho = 2.0 * W.e[s * W.vstride + mid - 1];
     for (int l = threadIdx.x; l < n; l += blockDim.x) {
         dd[l] = D[lo + l];
         z[l] = Z[(int64_t)(lo + l) * LD + (lo + l < mid ? mid - 1 : mid)] * 0.70710678118654752440;
+        mixed[l] = 0;
     }
     __syncthreads();
     for (int l = threadIdx.x; l < n; l += blockDim.x) {
@@ -671,22 +688,41 @@ dc_prepare_kernel(DcWork W, int level, const double* __restrict__ Dcur, const do
     int32_t* dfl = W.dfl + s * W.vstride + lo;
     stedc::Rotation* rot = W.rot + s * W.vstride + lo;
     __shared__ int sh_k;
+    int32_t* pos = W.pos + s * W.vstride + lo;
+    int32_t* ndg = W.ndg + s * W.vstride + lo;
     if (threadIdx.x == 0) {
         int nrot = 0;
-        const int k = stedc::deflation_scan(n, order, dd, z, rho, nd, dfl, rot, &nrot);
+        const int k = stedc::deflation_scan(n, order, dd, z, rho, nd, dfl, rot, &nrot, n1, mixed);
         sh_k = k;
         W.kc[s * nodes + t] = k;
         W.nr[s * nodes + t] = nrot;
+        // The eigenvector rows of the two children live in disjoint column ranges (except the few rows mixed by a
+        // rotation across the children), so the columns of U are grouped [first child | mixed | second child] and
+        // the merge is two products of half the width and about half the depth.
+        int k1 = 0, km = 0;
+        for (int q = 0; q < k; ++q) {
+            const int l = nd[q];
+            if (mixed[l]) ++km; else if (l < n1) ++k1;
+        }
+        int c1 = 0, cm = k1, c2 = k1 + km;
+        for (int q = 0; q < k; ++q) {
+            const int l = nd[q];
+            const int pq = mixed[l] ? cm++ : (l < n1 ? c1++ : c2++);
+            pos[q] = pq;
+            ndg[pq] = l;
+        }
         GemmTask g;
-        g.A = W.U + s * W.mstride + (int64_t)lo * LD + lo;
-        g.B = Z + (int64_t)lo * LD + lo;
-        g.C = Znew + s * W.mstride + (int64_t)lo * LD + lo;
-        g.bidx = nd;
-        g.M = k; g.N = n; g.K = k;
         g.lda = LD; g.ldb = LD; g.ldc = LD;
         g.kmodB = 0;
         g.alpha = 1.0; g.beta = 0.0;
-        W.tasks[s * nodes + t] = g;
+        g.M = k;
+        const double* Ub = W.U + s * W.mstride + (int64_t)lo * LD + lo;
+        const double* Zb = Z + (int64_t)lo * LD + lo;
+        double* Cb = Znew + s * W.mstride + (int64_t)lo * LD + lo;
+        g.A = Ub; g.B = Zb; g.C = Cb; g.bidx = ndg; g.N = n1; g.K = k1 + km;
+        W.tasks[(s * nodes + t) * 2] = g;
+        g.A = Ub + k1; g.B = Zb + n1; g.C = Cb + n1; g.bidx = ndg + k1; g.N = n - n1; g.K = k - k1;
+        W.tasks[(s * nodes + t) * 2 + 1] = g;
     }
     __syncthreads();
     const int k = sh_k;
@@ -744,7 +780,7 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(DcWork W, int level, do
     const double* w = W.w + s * W.vstride + lo;
     double* delta = W.U + s * W.mstride + (int64_t)(lo + j) * LD + lo;
     WarpLanes cx;
-    const double lam = stedc::secular_root(cx, k, j, dl, w, rho, delta);
+    const double lam = stedc::secular_root(cx, k, j, dl, w, rho, delta, W.pos + s * W.vstride + lo);
     if ((threadIdx.x & 31) == 0) Dnew[s * W.vstride + lo + j] = lam;
 }
 
@@ -764,8 +800,9 @@ __global__ void __launch_bounds__(1024) dc_zhat_kernel(DcWork W, int level) {
     double p = 1.0;
     if (i < k) {
         const double di = dl[i];
+        const int pi = W.pos[s * W.vstride + lo + i];   // column of entry i in the grouped matrix
         for (int j = jy; j < k; j += 32) {
-            const double num = U[(int64_t)j * LD + i];
+            const double num = U[(int64_t)j * LD + pi];
             p *= (j == i) ? num : num / (di - dl[j]);
         }
     }
@@ -789,11 +826,13 @@ __global__ void __launch_bounds__(256) dc_vectors_kernel(DcWork W, int level) {
     node_range(W.N, level, t, &lo, &hi);
     const int lane = threadIdx.x & 31;
     const double* zh = W.zh + s * W.vstride + lo;
+    const int32_t* pos = W.pos + s * W.vstride + lo;
     double* row = W.U + s * W.mstride + (int64_t)(lo + j) * LD + lo;
     double acc = 0.0;
     for (int i = lane; i < k; i += 32) {
-        const double u = zh[i] / row[i];
-        row[i] = u;
+        const int pi = pos[i];
+        const double u = zh[i] / row[pi];
+        row[pi] = u;
         acc += u * u;
     }
     acc = warp_sum(acc);
@@ -1060,10 +1099,10 @@ TrdPlan make_plan(int B, int N) {
 struct TrdWork {
     double *A, *Vt, *Z0, *Z1;          // [group][N][LD]; A doubles as U and X
     double *tau, *d, *e, *sgn, *D0, *D1, *dsc, *dl, *w, *zh;   // [group][LD]
-    int32_t *nd, *dfl, *rank;          // [group][LD]
+    int32_t *nd, *dfl, *rank, *pos, *ndg;   // [group][LD]
     stedc::Rotation* rot;              // [group][LD]
     int32_t *kc, *nr;                  // [group][2^L]
-    GemmTask* tasks;                   // [group][2^L]
+    GemmTask* tasks;                   // [group][2^L][2]
     GemmTask* wytasks;                 // [group][nblk]
     GemmTask* wtasks;                  // [nblk][group][wsplit]
     double *Gm, *T;                    // [group][nblk][wsplit][kWY][kWY] partial Gram matrices, [group][nblk][kWY][kWY]
@@ -1092,10 +1131,12 @@ void trd_carve(Arena& ar, TrdWork* w, int N, const TrdPlan& p) {
     w->nd = ar.take<int32_t>(g * v);
     w->dfl = ar.take<int32_t>(g * v);
     w->rank = ar.take<int32_t>(g * v);
+    w->pos = ar.take<int32_t>(g * v);
+    w->ndg = ar.take<int32_t>(g * v);
     w->rot = ar.take<stedc::Rotation>(g * v);
     w->kc = ar.take<int32_t>(g * nodes);
     w->nr = ar.take<int32_t>(g * nodes);
-    w->tasks = ar.take<GemmTask>(g * nodes);
+    w->tasks = ar.take<GemmTask>(g * nodes * 2);
     w->wytasks = ar.take<GemmTask>(g * p.nblk * p.wsplit);
     w->wtasks = ar.take<GemmTask>(g * p.nblk * p.wsplit);
     w->Gm = ar.take<double>(g * p.nblk * kWY * kWY * p.wsplit);
@@ -1148,7 +1189,7 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
     else if (trd_threads == 256) trd_fn = (const void*)sytrd_kernel<256>;
     else trd_threads = 512;
     SCB_CUDA(cudaFuncSetAttribute(trd_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    SCB_CUDA(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * N + 64));
+    SCB_CUDA(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * N + 64));
     const size_t lsmem = sizeof(double) * 2 * kLeaf * (kLeaf + 1);
     SCB_CUDA(cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
     const size_t tsmem = sizeof(double) * kWY * (kWY + 1);
@@ -1192,7 +1233,7 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
         DcWork W;
         W.N = N; W.LD = LD; W.L = L;
         W.d = w.d; W.e = w.e; W.sgn = w.sgn; W.D0 = w.D0; W.D1 = w.D1; W.Z0 = w.Z0; W.Z1 = w.Z1; W.U = w.A;
-        W.dsc = w.dsc; W.dl = w.dl; W.w = w.w; W.zh = w.zh; W.nd = w.nd; W.dfl = w.dfl; W.rot = w.rot;
+        W.dsc = w.dsc; W.dl = w.dl; W.w = w.w; W.zh = w.zh; W.nd = w.nd; W.dfl = w.dfl; W.pos = w.pos; W.ndg = w.ndg; W.rot = w.rot;
         W.kc = w.kc; W.nr = w.nr; W.tasks = w.tasks; W.vstride = vstride; W.mstride = mstride;
         dc_setup_kernel<<<live, 1024, 0, st>>>(W);
         SCB_LAUNCH_CHECK();
@@ -1204,7 +1245,7 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
             int lo, hi;
             node_range(N, level, (int)nodes - 1, &lo, &hi);   // the last node of a level is the largest
             const int nmax = hi - lo;
-            dc_prepare_kernel<<<dim3(nodes, (unsigned)live), 1024, 20 * (size_t)nmax + 64, st>>>(W, level, Dcur, Zcur, Znew);
+            dc_prepare_kernel<<<dim3(nodes, (unsigned)live), 1024, 21 * (size_t)nmax + 64, st>>>(W, level, Dcur, Zcur, Znew);
             SCB_LAUNCH_CHECK();
             dc_rotate_kernel<<<dim3((unsigned)ceil_div(nmax, 256), nodes, (unsigned)live), 256, 0, st>>>(W, level, Zcur);
             SCB_LAUNCH_CHECK();
@@ -1215,7 +1256,9 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
             dc_vectors_kernel<<<dim3((unsigned)ceil_div(nmax, 8), nodes, (unsigned)live), 256, 0, st>>>(W, level);
             SCB_LAUNCH_CHECK();
             // tasks are stored [matrix][node]: contiguous over the live matrices only if nodes is the stride
-            SCB_TRY((launch_gemm<true, false>(GemmTask{}, w.tasks, nmax, nmax, (int)nodes * live, 0, 0, 0, st)));
+            // two tasks per merge (left / right half of the columns); the right child is the larger one
+            SCB_TRY((launch_gemm<true, false>(GemmTask{}, w.tasks, nmax, nmax - ((nmax / 2) & ~1), (int)nodes * live * 2, 0, 0, 0,
+                                             st)));
             dc_copy_deflated_kernel<<<dim3((unsigned)nmax, nodes, (unsigned)live), 128, 0, st>>>(W, level, Zcur, Znew, Dnew);
             SCB_LAUNCH_CHECK();
             double* td = Dcur; Dcur = Dnew; Dnew = td;

@@ -50,8 +50,11 @@ struct Rotation {
 //          modified (rotations move weight between close eigenvalues)
 //   rho    2 |beta| > 0
 // Output: k survivors  nd[0..k) (ascending d), deflated entries dfl[0..n-k), rotations rot[0..*nrot).
+//   n1, mixed  optional: the first n1 entries belong to the first sub-problem; mixed[l] (zeroed by the caller) is
+//          set for survivors that absorbed weight from the OTHER sub-problem through a rotation -- their
+//          eigenvector rows are no longer confined to one half of the merged range
 SCB_HD int deflation_scan(int n, const int* order, double* d, double* z, double rho, int* nd, int* dfl,
-                          Rotation* rot, int* nrot) {
+                          Rotation* rot, int* nrot, int n1 = 0, unsigned char* mixed = nullptr) {
     double dmax = 0.0, zmax = 0.0;
     for (int i = 0; i < n; ++i) {
         dmax = fmax(dmax, fabs(d[i]));
@@ -86,6 +89,7 @@ SCB_HD int deflation_scan(int n, const int* order, double* d, double* z, double 
             z[pj] = 0.0;
             rot[nr].p = pj; rot[nr].q = nj; rot[nr].c = c; rot[nr].s = s;
             ++nr;
+            if (mixed && (((pj < n1) != (nj < n1)) || mixed[pj])) mixed[nj] = 1;
             const double dp = d[pj] * c * c + d[nj] * s * s;
             d[nj] = d[pj] * s * s + d[nj] * c * c;
             d[pj] = dp;
@@ -103,13 +107,14 @@ SCB_HD int deflation_scan(int n, const int* order, double* d, double* z, double 
 // One root of the secular equation.  dl[0..k) ascending and distinct, w[0..k) non-zero, rho > 0.
 // Returns lambda_j and writes delta[i] = dl[i] - lambda_j (accurate) for the lanes' share i = lane, lane+lanes, ...
 // Every lane of the context calls it with the same arguments and gets the same result.
+// pos (optional): delta[pos[i]] is written instead of delta[i] (columns of the eigenvector matrix grouped by child).
 template <class Ctx>
 SCB_HD double secular_root(const Ctx& cx, int k, int j, const double* dl, const double* w, double rho,
-                           double* delta) {
+                           double* delta, const int* pos = nullptr) {
     const int l0 = cx.lane(), nl = cx.lanes();
     if (k == 1) {
         const double t = rho * w[0] * w[0];
-        if (l0 == 0) delta[0] = -t;
+        if (l0 == 0) delta[pos ? pos[0] : 0] = -t;
         return dl[0] + t;
     }
     const double rhoinv = 1.0 / rho;
@@ -203,7 +208,7 @@ SCB_HD double secular_root(const Ctx& cx, int k, int j, const double* dl, const 
         if (next == tau) break;
         tau = next;
     }
-    for (int i = l0; i < k; i += nl) delta[i] = (dl[i] - dorg) - tau;
+    for (int i = l0; i < k; i += nl) delta[pos ? pos[i] : i] = (dl[i] - dorg) - tau;
     return dorg + tau;
 }
 
