@@ -16,7 +16,7 @@
 //     (re-packed every 128 columns as the trailing matrix shrinks), the rest is
 //     served from L2: the reduction never streams the matrix from HBM.  Groups
 //     of CTAs work on different matrices of a batch concurrently.
-//  2. divide and conquer (stedc_core.cuh): leaves of order <= 64 by Jacobi in
+//  2. divide and conquer (stedc_core.cuh): leaves of order <= 32 by Jacobi in
 //     shared memory, then per level  prepare (rank sort + deflation scan) ->
 //     rotate -> secular roots (warp per root) -> z-hat -> eigenvector matrix
 //     of the rank-one problem -> Z_new = U^T Z as FP64 tensor-core GEMMs
@@ -559,7 +559,7 @@ __global__ void trd_init_kernel(int N, int LD, const double* __restrict__ A, dou
 // ------------------------------------------------------------------------------------------------------------
 // 2. divide and conquer on the tridiagonal matrix
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kLeaf = 64;
+constexpr int kLeaf = 32;
 
 // node t of `level` (root = level 0) covers [lo, hi); all split points are even (16-byte aligned operand origins)
 __host__ __device__ inline void node_range(int N, int level, int t, int* lo, int* hi) {
@@ -613,9 +613,9 @@ __global__ void __launch_bounds__(1024) dc_setup_kernel(DcWork W) {
         }
 }
 
-__global__ void __launch_bounds__(512) dc_leaf_kernel(DcWork W) {
+__global__ void __launch_bounds__(256) dc_leaf_kernel(DcWork W) {
     constexpr int LDS = kLeaf + 1;
-    constexpr int NT = 512;
+    constexpr int NT = 256;
     extern __shared__ __align__(16) double lsm[];
     double* S = lsm;
     double* V = lsm + kLeaf * LDS;
@@ -687,7 +687,7 @@ dc_prepare_kernel(DcWork W, int level, const double* __restrict__ Dcur, const do
     int32_t* nd = W.nd + s * W.vstride + lo;
     int32_t* dfl = W.dfl + s * W.vstride + lo;
     stedc::Rotation* rot = W.rot + s * W.vstride + lo;
-    __shared__ int sh_k;
+    __shared__ int sh_k, sh_cnt[3];
     int32_t* pos = W.pos + s * W.vstride + lo;
     int32_t* ndg = W.ndg + s * W.vstride + lo;
     if (threadIdx.x == 0) {
@@ -696,21 +696,37 @@ dc_prepare_kernel(DcWork W, int level, const double* __restrict__ Dcur, const do
         sh_k = k;
         W.kc[s * nodes + t] = k;
         W.nr[s * nodes + t] = nrot;
-        // The eigenvector rows of the two children live in disjoint column ranges (except the few rows mixed by a
-        // rotation across the children), so the columns of U are grouped [first child | mixed | second child] and
-        // the merge is two products of half the width and about half the depth.
-        int k1 = 0, km = 0;
-        for (int q = 0; q < k; ++q) {
+    }
+    __syncthreads();
+    // The eigenvector rows of the two children live in disjoint column ranges (except the few rows mixed by a
+    // rotation across the children), so the columns of U are grouped [first child | mixed | second child] and the
+    // merge is two products of half the width and about half the depth.  Category of survivor q: 0 / 1 / 2.
+    {
+        const int k = sh_k;
+        int* cat = order;   // the sort order is dead: reuse it for the categories
+        for (int q = threadIdx.x; q < k; q += blockDim.x) {
             const int l = nd[q];
-            if (mixed[l]) ++km; else if (l < n1) ++k1;
+            cat[q] = mixed[l] ? 1 : (l < n1 ? 0 : 2);
         }
-        int c1 = 0, cm = k1, c2 = k1 + km;
-        for (int q = 0; q < k; ++q) {
-            const int l = nd[q];
-            const int pq = mixed[l] ? cm++ : (l < n1 ? c1++ : c2++);
+        __syncthreads();
+        if (threadIdx.x < 3) {   // category sizes
+            int cnt = 0;
+            for (int q = 0; q < k; ++q) cnt += (cat[q] == (int)threadIdx.x);
+            sh_cnt[threadIdx.x] = cnt;
+        }
+        __syncthreads();
+        const int off[3] = {0, sh_cnt[0], sh_cnt[0] + sh_cnt[1]};
+        for (int q = threadIdx.x; q < k; q += blockDim.x) {
+            const int cq = cat[q];
+            int r = 0;
+            for (int u = 0; u < q; ++u) r += (cat[u] == cq);
+            const int pq = off[cq] + r;
             pos[q] = pq;
-            ndg[pq] = l;
+            ndg[pq] = nd[q];
         }
+    }
+    if (threadIdx.x == 0) {
+        const int k = sh_k, k1 = sh_cnt[0], km = sh_cnt[1];
         GemmTask g;
         g.lda = LD; g.ldb = LD; g.ldc = LD;
         g.kmodB = 0;
@@ -914,17 +930,25 @@ wy_tfactor_kernel(int N, int64_t vstride, int nblk, int S, const double* __restr
     const double* tv = tau + s * vstride + j0;
     for (int q = threadIdx.x; q < kWY * LDT; q += blockDim.x) wsm[q] = 0.0;
     __syncthreads();
+    // G is symmetric: column a is read as ROW a (contiguous), staged in shared memory one step ahead
+    __shared__ double grow[2][kWY];
+    if (threadIdx.x < kWY) grow[0][threadIdx.x] = G[threadIdx.x];
+    __syncthreads();
     for (int a = 0; a < nb; ++a) {
         const double ta = tv[a];
+        const double* ga = grow[a & 1];
+        double nxt = 0.0;
+        if (a + 1 < nb && threadIdx.x < kWY) nxt = G[(int64_t)(a + 1) * kWY + threadIdx.x];
         // col[r] = -ta * sum_{c=r}^{a-1} T[r][c] G[c][a]   (T upper triangular)
         for (int r = threadIdx.x; r < a; r += blockDim.x) {
             double acc = 0.0;
-            for (int cidx = r; cidx < a; ++cidx) acc = fma(wsm[r * LDT + cidx], G[(int64_t)cidx * kWY + a], acc);
+            for (int cidx = r; cidx < a; ++cidx) acc = fma(wsm[r * LDT + cidx], ga[cidx], acc);
             col[r] = -ta * acc;
         }
         __syncthreads();
         for (int r = threadIdx.x; r < a; r += blockDim.x) wsm[r * LDT + a] = col[r];
         if (threadIdx.x == 0) wsm[a * LDT + a] = ta;
+        if (threadIdx.x < kWY) grow[(a + 1) & 1][threadIdx.x] = nxt;
         __syncthreads();
     }
     for (int q = threadIdx.x; q < kWY * kWY; q += blockDim.x) Tg[q] = wsm[(q / kWY) * LDT + q % kWY];
@@ -1237,7 +1261,7 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
         W.kc = w.kc; W.nr = w.nr; W.tasks = w.tasks; W.vstride = vstride; W.mstride = mstride;
         dc_setup_kernel<<<live, 1024, 0, st>>>(W);
         SCB_LAUNCH_CHECK();
-        dc_leaf_kernel<<<dim3(1u << L, (unsigned)live), 512, lsmem, st>>>(W);
+        dc_leaf_kernel<<<dim3(1u << L, (unsigned)live), 256, lsmem, st>>>(W);
         SCB_LAUNCH_CHECK();
         double *Dcur = w.D0, *Dnew = w.D1, *Zcur = w.Z0, *Znew = w.Z1;
         for (int level = L - 1; level >= 0; --level) {
