@@ -1095,13 +1095,14 @@ TrdPlan make_plan(int B, int N) {
     // CTA groups of the tridiagonalisation (matrices reduced concurrently).  The per-column cost is dominated by
     // latencies that do not shrink with the work, so more, smaller groups win as long as the matrices in flight
     // stay L2-resident (rows that do not fit the shared-memory cache are served from L2): N = 900, 64 matrices:
-    // 4 groups 118 ms, 8 groups 83 ms, 12 groups 79 ms, 16 groups 67..230 ms (L2 thrashing).  A single matrix
+    // 4 groups 118 ms, 8 groups 83 ms, 12 groups 79 ms, 16 groups 67..230 ms (L2 thrashing): 12 are chosen.  A single matrix
     // always gets every SM.
     p.ngroups = 1;
     const size_t vec = sizeof(double) * 3 * p.LD;
     {
         const size_t footprint = sizeof(double) * (size_t)N * p.LD;
-        int ng = (int)(((size_t)56 << 20) / footprint);
+        // the rows cached in shared memory (all SMs together ~27 MB) do not occupy L2
+        int ng = (int)((((size_t)56 << 20) + (size_t)sms * (kTrdSmemBudget - vec)) / footprint);
         if (ng > p.group) ng = p.group;
         while (ng > 1 && (sms / ng < 4 || ceil_div(N, sms / ng) > kTrdMaxRows)) --ng;
         if (ng >= 1) p.ngroups = ng;
