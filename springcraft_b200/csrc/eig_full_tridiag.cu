@@ -1112,6 +1112,10 @@ TrdPlan make_plan(int B, int N) {
         if (ng >= 1 && ng <= 37 && ceil_div(N, sms / ng) <= kTrdMaxRows) p.ngroups = ng < p.group ? ng : p.group;
     }
     p.G = sms / p.ngroups;
+    if (const char* env = getenv("SCB_TRD_G")) {   // A/B switch: CTAs per matrix
+        const int g = atoi(env);
+        if (g >= 1 && g <= p.G && ceil_div(N, g) <= kTrdMaxRows) p.G = g;
+    }
     if (p.G > N) p.G = N;
     // X V_b has only N/128 x 1 tiles: split K until the launch fills the GPU
     p.wsplit = 1;
