@@ -285,7 +285,7 @@ int scb_rand_block(int64_t total, uint64_t seed, double *X, void *stream);
 /* full symmetric eigendecomposition of dense A[B][N][N] (lower triangle is
  * referenced, like LAPACK dsyevd behind np.linalg.eigh): eigval[B][N] ascending,
  * modes[B][N][N] with ROW k = mode k (nma.py:63).  A is destroyed.
- * N <= 64: Jacobi in shared memory; N <= 256: block Jacobi; larger N: Householder
+ * N <= 64: Jacobi in shared memory; larger N (up to 9,200): Householder
  * tridiagonalisation (one persistent cooperative kernel) + divide and conquer +
  * compact-WY back-transformation on the FP64 tensor cores; no host synchronisation.
  * Matrices of a batch share every launch. */

@@ -3,8 +3,8 @@
 //
 //  * N <= 64  : one CTA per matrix, two-sided cyclic Jacobi entirely in shared
 //               memory (the Rayleigh-Ritz kernel with S = I).
-//  * 64 < N <= 256 : block Jacobi in global memory -- see eig_full_block.cu.
-//  * N > 256  : tridiagonalisation + divide and conquer + back-transformation -- see eig_full_tridiag.cu.
+//  * N > 64   : tridiagonalisation + divide and conquer + back-transformation -- see eig_full_tridiag.cu
+//               (N <= 9,200; beyond that, or without cooperative launch: block Jacobi, eig_full_block.cu).
 #include <stdlib.h>
 
 #include "subspace.cuh"

@@ -1183,7 +1183,10 @@ bool eig_full_tridiag_supported(int N) {
     // be able to keep one CTA per SM co-resident (cooperative launch); otherwise the block-Jacobi solver is used
     const size_t LD = (size_t)((N + 3) & ~3);
     // (N <= 9,200: the three vectors alone fill the shared memory, rows are then cached only once they have shrunk)
-    if (N <= 256 || sizeof(double) * 3 * LD + 2048 > kTrdSmemBudget) return false;
+    // (block Jacobi is 3-5x slower already at N = 72...256: 3.7 / 6.4 ms against 0.8 / 2.2 ms)
+    int min_n = 64;
+    if (const char* env = getenv("SCB_TRD_MIN_N")) min_n = atoi(env) >= 33 ? atoi(env) : 33;   // A/B switch
+    if (N <= min_n || sizeof(double) * 3 * LD + 2048 > kTrdSmemBudget) return false;
     int dev = 0, coop = 1, smem = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) coop = 1;

@@ -251,8 +251,8 @@ def test_c2_chain1000_full_spectrum():
 
 @pytest.mark.parametrize("N", [65, 128, 200, 331])
 def test_eig_full_block_random(N):
-    """Block-Jacobi full eigensolver vs LAPACK on random symmetric matrices
-    (including a rank-deficient PSD one), lower triangle referenced."""
+    """Full eigensolver (N > 64: tridiagonalisation + divide and conquer) vs LAPACK on random symmetric matrices
+    of small order (including a rank-deficient PSD one), lower triangle referenced."""
     import torch
     from springcraft_b200 import _engine
     rng = np.random.default_rng(N)
@@ -354,6 +354,19 @@ def test_eig_full_tridiag_batched():
     lam, modes = lam.cpu().numpy(), modes.cpu().numpy()
     for A, l, m in zip(mats, lam, modes):
         _check_full(A, l, m, tol=2e-13)
+
+
+def test_eig_full_block_jacobi_fallback(monkeypatch):
+    """The two-sided block Jacobi solver (round 1) stays as the fallback for orders the tridiagonal solver does not
+    take (N > 9,200, devices without cooperative launch); SCB_EIG_FULL=jacobi selects it."""
+    import torch
+    from springcraft_b200 import _engine
+    monkeypatch.setenv("SCB_EIG_FULL", "jacobi")
+    rng = np.random.default_rng(9)
+    N = 200
+    A = rng.normal(size=(N, N)); A = A + A.T
+    lam, modes = _engine.eig_full_dense(torch.from_numpy(A.copy()).cuda())
+    _check_full(A, lam[0].cpu().numpy(), modes[0].cpu().numpy(), tol=1e-12)
 
 
 def test_eig_full_block_batched():
