@@ -356,6 +356,44 @@ def test_eig_full_tridiag_batched():
         _check_full(A, l, m, tol=2e-13)
 
 
+def test_eig_full_tridiag_fuzz():
+    """Seeded fuzz of the full-spectrum solver: random orders 65..500 (odd and even: both alignment paths of the
+    grouped merge products), batches of 1..4, eight kinds of spectra (indefinite, rank deficient, two clusters 1e-10
+    apart, decoupled blocks, banded, almost diagonal, integer eigenvalues with high multiplicity, negative definite)."""
+    import torch
+    from springcraft_b200 import _engine
+    rng = np.random.default_rng(2024)
+    kinds = ["rand", "psd_def", "clustered", "blocks", "band", "sparse_diag", "repeat", "neg"]
+    for it in range(16):
+        N = int(rng.integers(65, 500))
+        B = int(rng.integers(1, 5))
+        kind = kinds[it % len(kinds)]
+        mats = []
+        for _ in range(B):
+            M = rng.standard_normal((N, N)); A = M + M.T
+            if kind == "psd_def":
+                G = rng.standard_normal((N, int(rng.integers(1, N)))); A = G @ G.T
+            elif kind == "clustered":
+                Q, _ = np.linalg.qr(M)
+                lam = np.concatenate([np.ones(N // 2), 1 + 1e-10 * rng.standard_normal(N - N // 2)])
+                A = (Q * lam) @ Q.T; A = (A + A.T) / 2
+            elif kind == "blocks":
+                c = int(rng.integers(1, N - 1)); A[:c, c:] = 0; A[c:, :c] = 0
+            elif kind == "band":
+                bw = int(rng.integers(1, 6)); A = np.triu(np.tril(A, bw), -bw)
+            elif kind == "sparse_diag":
+                A = np.diag(rng.standard_normal(N)); i, j = rng.integers(0, N, 2); A[i, j] = A[j, i] = 0.5
+            elif kind == "repeat":
+                Q, _ = np.linalg.qr(M); A = (Q * rng.integers(0, 4, N).astype(float)) @ Q.T; A = (A + A.T) / 2
+            elif kind == "neg":
+                A = -np.abs(A) - 5 * np.eye(N)
+            mats.append(A)
+        lam, modes = _engine.eig_full_dense(torch.from_numpy(np.stack(mats)).cuda())
+        lam, modes = lam.cpu().numpy(), modes.cpu().numpy()
+        for A, l, m in zip(mats, lam, modes):
+            _check_full(A, l, m, tol=5e-13)
+
+
 def test_eig_full_block_jacobi_fallback(monkeypatch):
     """The two-sided block Jacobi solver (round 1) stays as the fallback for orders the tridiagonal solver does not
     take (N > 9,200, devices without cooperative launch); SCB_EIG_FULL=jacobi selects it."""
