@@ -24,5 +24,5 @@ cap slab dense_slab_apply_kernel 1 slab
 cap tf32 dense_slab_tf32_kernel 1 tf32
 fi
 cap sytrd sytrd_kernel 1 full          # the whole tridiagonalisation is ONE launch
-cap dcgemm dgemm_dmma_kernel 84 full  # 79 GEMM launches per call: #84 = top-level merge of the second call (M = N = K ~ 3,000)
+cap dcgemm dgemm_dmma_kernel 63 full  # 57 GEMM launches per call (7 merge levels + Gram + T_b V_b^T + 24 x 2): #63 = top-level merge of the second call
 ls -la gpurun_out/${TAG}_*.ncu-rep
