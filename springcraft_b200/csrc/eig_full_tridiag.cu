@@ -272,7 +272,8 @@ __device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, un
 // (Measured dead end: letting the exchanged values carry their own arrival flag -- every slot armed with a NaN
 // payload and polled by its consumers, no barrier -- is SLOWER than the barrier below: 148 x 1024 threads spinning
 // on shared lines delay the producers' stores; C2 65 ms instead of 51 ms.)
-// Also measured and dropped: fence.acq_rel + relaxed polling instead of __threadfence() + acquire polling (C2 41.9
+// Also measured and dropped: four rows per pass task sharing the vector loads (C2 38.9 against 38.5 ms, 64 x N=900
+// 65.9 against 61.5 ms), fence.acq_rel + relaxed polling instead of __threadfence() + acquire polling (C2 41.9
 // against 40.4 ms), two co-resident 256-thread CTAs per SM (no gain), and one 16-CTA thread-block cluster
 // per matrix with the exchange pushed through DSMEM and the hardware cluster barrier (64 x N=900: 98 ms against
 // 89 ms; 256 x N=300: 69 ms against 35 ms -- the per-column cost is the CTA's own chain of reductions).
