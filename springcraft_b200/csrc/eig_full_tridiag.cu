@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
         double* ee = P.e + (size_t)s * LD;
         int cache_col0 = 0, cache_len = LD, cache_rows = 0;
         double tau_prev = 0.0;
+        // tracked incrementally (no division by G in the column loop): owner = j % G, rmin_j = first owned row > j
+        int owner = 0, rmin_j = (c == 0) ? 1 : 0, seg_np = -1, seg_nc = -1, seg_n = 1;
         for (int i = tid; i < 3 * LD; i += kTrdThreads) tsm[i] = 0.0;   // the padding [N, LD) of the vectors stays zero
         __syncthreads();
 
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                     if (tid == 1) vcur[j + 1] = 1.0;   // thread 1 owns component j+1
                 }
                 __syncthreads();
-                if ((j % G) == c) {
+                if (owner == c) {
                     if (tid == 0) {
                         dd[j] = dj;
                         if (j < N - 1) { ee[j] = beta; tau[j] = tau_cur; }
@@ -441,26 +443,27 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 //      Task = (pair of rows, column segment); a lane handles two adjacent columns of both rows.
                 double* pout = xch_all + (size_t)(j % kXchBufs) * 2 * LD;   // replica 0; replica k at + k * xcopy
                 double* cout = pout + LD;
-                const int rmin = (j + 1 > c) ? (j + 1 - c + G - 1) / G : 0;
+                const int rmin = rmin_j;
                 const int na = nown - rmin;                   // rows alive
                 const int npairs = (na + 1) >> 1;
                 const int cb = (j + 1) & ~1;                  // first column pair (if it starts at column j: vcur[j] == 0)
                 const int nchunk = (LD - cb + 63) >> 6;       // chunks of 64 columns
                 // column segments per row pair: minimise (rounds of the warps) x (segment length); a segment keeps
                 // at least one full set of chunks in flight (11 pairs on 16 warps: 4 segments = 3 rounds of 1/4)
-                int nseg = 1;
-                {
+                if (npairs != seg_np || nchunk != seg_nc) {   // changes every ~32 columns only
                     constexpr int nw = kTrdThreads / 32;
                     int best = 1 << 30;
+                    seg_np = npairs; seg_nc = nchunk; seg_n = 1;
 #pragma unroll   // divisions by compile-time constants
                     for (int sgc = 1; sgc <= kTrdMaxSeg; ++sgc) {
                         if (npairs <= 0) break;
                         const int len = (nchunk + sgc - 1) / sgc;
                         if (sgc > 1 && len < UNR) break;
                         const int cost = ((npairs * sgc + nw - 1) / nw) * ((len + UNR - 1) / UNR);
-                        if (cost < best) { best = cost; nseg = sgc; }
+                        if (cost < best) { best = cost; seg_n = sgc; }
                     }
                 }
+                const int nseg = seg_n;
                 const int cps = (nchunk + nseg - 1) / nseg;
                 for (int task = warp; task < npairs * nseg; task += kTrdThreads / 32) {
                     const int pr = task / nseg, sg = task - pr * nseg;
@@ -532,6 +535,8 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 TRD_LAP(t_bar);
                 double* tmp = vprev; vprev = vcur; vcur = tmp;
                 tau_prev = tau_cur;
+                if (++owner == G) owner = 0;
+                if (c + G * rmin_j <= j + 1) ++rmin_j;   // row c + G rmin_j is dead from column j+1 on
             }
         }
         ++epoch;
