@@ -1,8 +1,8 @@
-// K3c (N > 128): full symmetric eigendecomposition by reduction to tridiagonal
+// K3c (64 < N <= 9,200): full symmetric eigendecomposition by reduction to tridiagonal
 // form, divide and conquer on the tridiagonal matrix, and back-transformation.
 // Replaces LAPACK dsyevd behind np.linalg.eigh (nma.py:61) and np.linalg.pinv
 // (anm.py:135) when every mode is requested; the two-sided block Jacobi of
-// eig_full_block.cu (145 N^3 flop) stays for small orders only.
+// eig_full_block.cu (145 N^3 flop) stays as the fallback for larger orders.
 //
 //  1. sytrd_kernel -- Householder tridiagonalisation, ONE persistent
 //     cooperative launch.  The rows of the (full, symmetric) matrix are dealt

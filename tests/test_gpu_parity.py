@@ -283,7 +283,7 @@ def _check_full(A, lam, modes, tol=1e-12):
 
 @pytest.mark.parametrize("N", [257, 300, 515, 1001])
 def test_eig_full_tridiag_random(N):
-    """N > 256: Householder tridiagonalisation + divide and conquer + back-transformation (eig_full_tridiag.cu)
+    """N > 64: Householder tridiagonalisation + divide and conquer + back-transformation (eig_full_tridiag.cu)
     vs LAPACK (np.linalg.eigh, reference nma.py:61): random symmetric matrices of even and odd order, lower
     triangle referenced, 1e-13-class eigenvalues, orthogonality and residuals."""
     import torch
