@@ -1118,10 +1118,6 @@ TrdPlan make_plan(int B, int N) {
         if (ng >= 1 && ng <= 37 && ceil_div(N, sms / ng) <= kTrdMaxRows) p.ngroups = ng < p.group ? ng : p.group;
     }
     p.G = sms / p.ngroups;
-    if (const char* env = getenv("SCB_TRD_G")) {   // A/B switch: CTAs per matrix
-        const int g = atoi(env);
-        if (g >= 1 && g <= p.G && ceil_div(N, g) <= kTrdMaxRows) p.G = g;
-    }
     if (p.G > N) p.G = N;
     // X V_b has only N/128 x 1 tiles: split K until the launch fills the GPU
     p.wsplit = 1;
@@ -1190,9 +1186,7 @@ bool eig_full_tridiag_supported(int N) {
     const size_t LD = (size_t)((N + 3) & ~3);
     // (N <= 9,200: the three vectors alone fill the shared memory, rows are then cached only once they have shrunk)
     // (block Jacobi is 3-5x slower already at N = 72...256: 3.7 / 6.4 ms against 0.8 / 2.2 ms)
-    int min_n = 64;
-    if (const char* env = getenv("SCB_TRD_MIN_N")) min_n = atoi(env) >= 33 ? atoi(env) : 33;   // A/B switch
-    if (N <= min_n || sizeof(double) * 3 * LD + 2048 > kTrdSmemBudget) return false;
+    if (N <= 64 || sizeof(double) * 3 * LD + 2048 > kTrdSmemBudget) return false;
     int dev = 0, coop = 1, smem = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) coop = 1;
@@ -1220,12 +1214,9 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
     if (!ar.ok()) return SCB_ERR_WORKSPACE;
     const int LD = p.LD, L = p.L;
     const int64_t mstride = (int64_t)N * LD, vstride = LD;
-    int trd_threads = 512;
-    if (const char* env = getenv("SCB_TRD_THREADS")) trd_threads = atoi(env);
+    // 512 threads per CTA: 1,024 (register spills, barrier skew) and 256 (too few warps for the row pass) were slower
+    constexpr int trd_threads = 512;
     const void* trd_fn = (const void*)sytrd_kernel<512>;
-    if (trd_threads == 1024) trd_fn = (const void*)sytrd_kernel<1024>;
-    else if (trd_threads == 256) trd_fn = (const void*)sytrd_kernel<256>;
-    else trd_threads = 512;
     SCB_CUDA(cudaFuncSetAttribute(trd_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     SCB_CUDA(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * N + 64));
     const size_t lsmem = sizeof(double) * 2 * kLeaf * (kLeaf + 1);
