@@ -111,7 +111,10 @@ extern "C" int stedc_host(int N, const double* d_in, const double* e_in, double*
                 order[r] = l;
             }
             int nrot = 0;
-            const int k = deflation_scan(n, order.data(), dd.data(), z.data(), rho, nd.data(), dfl.data(), rot.data(), &nrot);
+            const int n1 = mid - lo;
+            std::vector<unsigned char> mixed(n, 0);
+            const int k = deflation_scan(n, order.data(), dd.data(), z.data(), rho, nd.data(), dfl.data(), rot.data(), &nrot,
+                                         n1, mixed.data());
             stats[0] += n - k; stats[1] += nrot; stats[2] += n;
             for (int r = 0; r < nrot; ++r) {
                 double* x = &Za[(size_t)(lo + rot[r].p) * N + lo];
@@ -122,27 +125,46 @@ extern "C" int stedc_host(int N, const double* d_in, const double* e_in, double*
                     y[i] = rot[r].c * b - rot[r].s * a;
                 }
             }
+            // columns of U grouped [first child | mixed by a rotation across the children | second child], as on the GPU
+            std::vector<int> pos(k), ndg(k);
+            int k1 = 0, km = 0;
+            for (int q = 0; q < k; ++q) { if (mixed[nd[q]]) ++km; else if (nd[q] < n1) ++k1; }
+            {
+                int c1 = 0, cm = k1, c2 = k1 + km;
+                for (int q = 0; q < k; ++q) {
+                    const int l = nd[q];
+                    const int pq = mixed[l] ? cm++ : (l < n1 ? c1++ : c2++);
+                    pos[q] = pq; ndg[pq] = l;
+                }
+            }
             for (int l = 0; l < k; ++l) { dl[l] = dd[nd[l]]; w[l] = z[nd[l]]; }
             OneLane cx;
-            for (int j = 0; j < k; ++j) Dn[lo + j] = secular_root(cx, k, j, dl.data(), w.data(), rho, &U[(size_t)j * N]);
+            for (int j = 0; j < k; ++j)
+                Dn[lo + j] = secular_root(cx, k, j, dl.data(), w.data(), rho, &U[(size_t)j * N], pos.data());
             for (int i = 0; i < k; ++i) {
-                double p = U[(size_t)i * N + i];
-                for (int j = 0; j < k; ++j) if (j != i) p *= U[(size_t)j * N + i] / (dl[i] - dl[j]);
+                double p = U[(size_t)i * N + pos[i]];
+                for (int j = 0; j < k; ++j) if (j != i) p *= U[(size_t)j * N + pos[i]] / (dl[i] - dl[j]);
                 zh[i] = std::copysign(std::sqrt(std::fabs(p)), w[i]);
             }
             for (int j = 0; j < k; ++j) {
                 double s = 0.0;
-                for (int i = 0; i < k; ++i) { const double u = zh[i] / U[(size_t)j * N + i]; U[(size_t)j * N + i] = u; s += u * u; }
+                for (int i = 0; i < k; ++i) { const double u = zh[i] / U[(size_t)j * N + pos[i]]; U[(size_t)j * N + pos[i]] = u; s += u * u; }
                 s = 1.0 / std::sqrt(s);
                 for (int i = 0; i < k; ++i) U[(size_t)j * N + i] *= s;
             }
+            // two half products: columns [0, n1) from the groups [first | mixed], columns [n1, n) from [mixed | second]
             for (int j = 0; j < k; ++j) {
                 double* out = &Zb[(size_t)(lo + j) * N + lo];
                 std::fill(out, out + n, 0.0);
-                for (int l = 0; l < k; ++l) {
-                    const double u = U[(size_t)j * N + l];
-                    const double* src = &Za[(size_t)(lo + nd[l]) * N + lo];
-                    for (int i = 0; i < n; ++i) out[i] += u * src[i];
+                for (int g = 0; g < k1 + km; ++g) {
+                    const double u = U[(size_t)j * N + g];
+                    const double* src = &Za[(size_t)(lo + ndg[g]) * N + lo];
+                    for (int i = 0; i < n1; ++i) out[i] += u * src[i];
+                }
+                for (int g = k1; g < k; ++g) {
+                    const double u = U[(size_t)j * N + g];
+                    const double* src = &Za[(size_t)(lo + ndg[g]) * N + lo];
+                    for (int i = n1; i < n; ++i) out[i] += u * src[i];
                 }
             }
             for (int q = 0; q < n - k; ++q) {
