@@ -98,15 +98,30 @@ pair_fill_kernel(int n, int np, int64_t total_pairs, const int64_t* __restrict__
     const int64_t b0 = (2 * t + 1 < n) ? rowptr[r1] : 0;
     PairEntry<D>* ent = pent + a0 + 2 * g;
     const int total = pcount[g] * V;
-    for (int idx = lane; idx < total; idx += 32) {
-        const int e = idx / V, q = idx - e * V;
-        const bool low = q >= DD;
-        const int src = low ? ent[e].pad[1] : ent[e].pad[0];
-        const int qq = low ? q - DD : q;
-        double v = 0.0;
-        if (src == kSrcDiag) v = diag[(low ? r1 : r0) * DD + qq];
-        else if (src != kSrcNone) v = offdiag[((low ? b0 : a0) + src) * DD + qq];
-        ent[e].blk[q] = v;
+    // four independent (header -> block value -> store) chains in flight per lane: the copy is latency-bound otherwise
+    for (int base = lane; base < total; base += 128) {
+        int e[4], q[4], src[4];
+        bool low[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + 32 * u;
+            e[u] = idx / V;
+            q[u] = idx - e[u] * V;
+            low[u] = q[u] >= DD;
+            src[u] = kSrcNone;
+            if (idx < total) src[u] = low[u] ? ent[e[u]].pad[1] : ent[e[u]].pad[0];
+        }
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int qq = low[u] ? q[u] - DD : q[u];
+            v[u] = 0.0;
+            if (src[u] == kSrcDiag) v[u] = diag[(low[u] ? r1 : r0) * DD + qq];
+            else if (src[u] != kSrcNone) v[u] = offdiag[((low[u] ? b0 : a0) + src[u]) * DD + qq];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (base + 32 * u < total) ent[e[u]].blk[q[u]] = v[u];
     }
 }
 
