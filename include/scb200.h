@@ -287,7 +287,8 @@ int scb_rand_block(int64_t total, uint64_t seed, double *X, void *stream);
  * modes[B][N][N] with ROW k = mode k (nma.py:63).  A is destroyed.
  * N <= 64: Jacobi in shared memory; larger N (up to 9,200): Householder
  * tridiagonalisation (one persistent cooperative kernel) + divide and conquer +
- * compact-WY back-transformation on the FP64 tensor cores; no host synchronisation.
+ * compact-WY back-transformation on the FP64 tensor cores; the host reads back one
+ * status word at the end (the call returns after the work has completed).
  * Matrices of a batch share every launch. */
 size_t scb_eig_full_workspace_bytes(int B, int N);
 int scb_eig_full(int B, int N, double *A, double *eigval, double *modes,

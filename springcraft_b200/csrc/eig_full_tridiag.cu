@@ -23,7 +23,7 @@
 //     (all merges of a level and all matrices of a batch in one launch each).
 //  3. back-transformation X <- X (I - V T V^T) by compact-WY blocks of 128
 //     reflectors: three DMMA GEMMs per block.
-// No host synchronisation anywhere: every data-dependent size (survivors of a
+// No host read-back while the solver runs (one status word at the end): every data-dependent size (survivors of a
 // deflation, rotations) stays on the device.
 #include <stdlib.h>
 
