@@ -19,10 +19,12 @@
 //  2. divide and conquer (stedc_core.cuh): leaves of order <= 32 by Jacobi in
 //     shared memory, then per level  prepare (rank sort + deflation scan) ->
 //     rotate -> secular roots (warp per root) -> z-hat -> eigenvector matrix
-//     of the rank-one problem -> Z_new = U^T Z as FP64 tensor-core GEMMs
-//     (all merges of a level and all matrices of a batch in one launch each).
-//  3. back-transformation X <- X (I - V T V^T) by compact-WY blocks of 128
-//     reflectors: three DMMA GEMMs per block.
+//     of the rank-one problem -> Z_new = U^T Z as FP64 tensor-core GEMMs, two
+//     half-width products per merge (columns of U grouped by child); all merges
+//     of a level and all matrices of a batch share each launch.
+//  3. back-transformation x^T <- x^T (I - V_b T_b^T V_b^T) by compact-WY blocks of 128
+//     reflectors, last block first: T_b V_b^T for all blocks in one batched GEMM, then
+//     per block a split-K product X (T_b V_b^T)^T, a small reduction and a rank-128 update.
 // No host read-back while the solver runs (one status word at the end): every data-dependent size (survivors of a
 // deflation, rotations) stays on the device.
 #include <stdlib.h>
