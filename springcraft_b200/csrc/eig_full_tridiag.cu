@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                         if (npairs <= 0) break;
                         const int len = (nchunk + sgc - 1) / sgc;
                         if (sgc > 1 && len < UNR) break;
-                        const int cost = ((npairs * sgc + nw - 1) / nw) * ((len + UNR - 1) / UNR);
+                        // + 4: set-up and the two warp reductions of a task cost about eight loop iterations
+                        const int cost = ((npairs * sgc + nw - 1) / nw) * ((len + UNR - 1) / UNR + 8);
                         if (cost < best) { best = cost; seg_n = sgc; }
                     }
                 }
