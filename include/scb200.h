@@ -293,6 +293,15 @@ int scb_rand_block(int64_t total, uint64_t seed, double *X, void *stream);
 size_t scb_eig_full_workspace_bytes(int B, int N);
 int scb_eig_full(int B, int N, double *A, double *eigval, double *modes,
                  void *workspace, size_t workspace_bytes, void *stream);
+/* the same with an explicit solver: the tridiagonal solver is a cooperative launch
+ * that needs every SM of the device; a caller whose other streams hold SMs for an
+ * unknown time can ask for SCB_EIG_JACOBI (ordinary launches only) */
+#define SCB_EIG_AUTO 0
+#define SCB_EIG_JACOBI 1
+#define SCB_EIG_TRIDIAG 2
+size_t scb_eig_full_workspace_bytes_ex(int solver, int B, int N);
+int scb_eig_full_ex(int solver, int B, int N, double *A, double *eigval, double *modes,
+                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K4  fluctuation / covariance products (nma.py:108-359, 422-473).

@@ -251,9 +251,14 @@ class DeviceModel:
         return eigval, X, resid, iters, Z
 
 
-def eig_full_dense(A):
+_EIG_SOLVERS = {"auto": 0, "jacobi": 1, "tridiag": 2}
+
+
+def eig_full_dense(A, solver="auto"):
     """Full eigendecomposition of dense symmetric device matrices A[B][N][N]
-    (destroyed).  Returns (eigval[B][N], modes[B][N][N]) with rows = modes."""
+    (destroyed).  Returns (eigval[B][N], modes[B][N][N]) with rows = modes.
+    ``solver``: "auto" (tridiagonalisation + divide and conquer for N > 64), "jacobi" (block Jacobi: ordinary
+    launches only, for callers whose other streams keep SMs busy for an unknown time) or "tridiag"."""
     torch = _torch()
     h = _lib.require_device()
     if A.dim() == 2:
@@ -261,10 +266,11 @@ def eig_full_dense(A):
     B, N = int(A.shape[0]), int(A.shape[1])
     eigval = torch.empty((B, N), dtype=torch.float64, device="cuda")
     modes = torch.empty((B, N, N), dtype=torch.float64, device="cuda")
-    ws_bytes = h.scb_eig_full_workspace_bytes(B, N)
+    code = _EIG_SOLVERS[solver]
+    ws_bytes = h.scb_eig_full_workspace_bytes_ex(code, B, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-    _lib.check(h.scb_eig_full(B, N, _lib.ptr(A), _lib.ptr(eigval), _lib.ptr(modes), _lib.ptr(ws), ws_bytes,
-                              _lib.stream_ptr()))
+    _lib.check(h.scb_eig_full_ex(code, B, N, _lib.ptr(A), _lib.ptr(eigval), _lib.ptr(modes), _lib.ptr(ws), ws_bytes,
+                                 _lib.stream_ptr()))
     return eigval, modes
 
 

@@ -113,6 +113,8 @@ SIGNATURES = {
     "scb_rand_block": (_I, [_I64, _U64, _P, _P]),
     "scb_eig_full_workspace_bytes": (_SZ, [_I, _I]),
     "scb_eig_full": (_I, [_I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "scb_eig_full_workspace_bytes_ex": (_SZ, [_I, _I, _I]),
+    "scb_eig_full_ex": (_I, [_I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "scb_msf": (_I, [_I, _I, _I, _I, _P, _P, _D, _P, _P]),
     "scb_msf_cols": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _D, _P, _P]),
     "scb_dcc": (_I, [_I, _I, _I, _P, _P, _I, _D, _I, _I, _P, _P, _SZ, _P]),

@@ -20,9 +20,12 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
                      cudaStream_t st);
 size_t eig_full_tridiag_workspace_bytes(int B, int N);
 
-// SCB_EIG_FULL=jacobi forces the block-Jacobi solver (A/B measurements)
-static bool use_tridiag(int N) {
-    if (!eig_full_tridiag_supported(N)) return false;
+// solver: SCB_EIG_AUTO / SCB_EIG_JACOBI / SCB_EIG_TRIDIAG.  SCB_EIG_FULL=jacobi forces the block-Jacobi solver in
+// automatic mode (A/B measurements).  The tridiagonal solver is a cooperative launch that needs every SM: a caller
+// whose other streams keep SMs busy for an unknown time can ask for the block-Jacobi solver (ordinary launches).
+static bool use_tridiag(int N, int solver) {
+    if (solver == SCB_EIG_JACOBI || !eig_full_tridiag_supported(N)) return false;
+    if (solver == SCB_EIG_TRIDIAG) return true;
     const char* env = getenv("SCB_EIG_FULL");
     if (env && env[0] == 'j') return false;
     return true;
@@ -57,21 +60,24 @@ __global__ void unpad_modes_kernel(int N, int P, const double* __restrict__ C, c
 
 using namespace scb;
 
-extern "C" size_t scb_eig_full_workspace_bytes(int B, int N) {
+extern "C" size_t scb_eig_full_workspace_bytes_ex(int solver, int B, int N) {
     if (N <= 64) {
         const size_t P = N <= 32 ? 32 : 64;
         return 3 * (((size_t)B * P * P * sizeof(double) + 255) & ~size_t(255)) +
                (((size_t)B * P * sizeof(double) + 255) & ~size_t(255)) + 256;
     }
-    if (use_tridiag(N)) return eig_full_tridiag_workspace_bytes(B, N);
+    if (use_tridiag(N, solver)) return eig_full_tridiag_workspace_bytes(B, N);
     return eig_full_block_workspace_bytes(B, N);
 }
 
-extern "C" int scb_eig_full(int B, int N, double* A, double* eigval, double* modes, void* workspace,
-                            size_t workspace_bytes, void* stream) {
-    if (!A || !eigval || !modes || !workspace || B < 1 || N < 1) return SCB_ERR_INVALID;
+extern "C" size_t scb_eig_full_workspace_bytes(int B, int N) { return scb_eig_full_workspace_bytes_ex(SCB_EIG_AUTO, B, N); }
+
+extern "C" int scb_eig_full_ex(int solver, int B, int N, double* A, double* eigval, double* modes, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!A || !eigval || !modes || !workspace || B < 1 || N < 1 || solver < SCB_EIG_AUTO || solver > SCB_EIG_TRIDIAG)
+        return SCB_ERR_INVALID;
     cudaStream_t st = as_stream(stream);
-    if (N > 64 && use_tridiag(N)) return eig_full_tridiag(B, N, A, eigval, modes, workspace, workspace_bytes, st);
+    if (N > 64 && use_tridiag(N, solver)) return eig_full_tridiag(B, N, A, eigval, modes, workspace, workspace_bytes, st);
     if (N > 64) return eig_full_block(B, N, A, eigval, modes, workspace, workspace_bytes, st);
     const int P = N <= 32 ? 32 : 64;
     Arena ar(workspace, workspace_bytes);
@@ -88,4 +94,9 @@ extern "C" int scb_eig_full(int B, int N, double* A, double* eigval, double* mod
     unpad_modes_kernel<<<g2, 256, 0, st>>>(N, P, C, theta, modes, eigval);
     SCB_LAUNCH_CHECK();
     return SCB_OK;
+}
+
+extern "C" int scb_eig_full(int B, int N, double* A, double* eigval, double* modes, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    return scb_eig_full_ex(SCB_EIG_AUTO, B, N, A, eigval, modes, workspace, workspace_bytes, stream);
 }

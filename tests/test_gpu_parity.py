@@ -405,6 +405,11 @@ def test_eig_full_block_jacobi_fallback(monkeypatch):
     A = rng.normal(size=(N, N)); A = A + A.T
     lam, modes = _engine.eig_full_dense(torch.from_numpy(A.copy()).cuda())
     _check_full(A, lam[0].cpu().numpy(), modes[0].cpu().numpy(), tol=1e-12)
+    # the explicit selector of the ABI (scb_eig_full_ex): what the dense row-slab solver asks for on several ranks
+    monkeypatch.delenv("SCB_EIG_FULL")
+    for solver in ("jacobi", "tridiag", "auto"):
+        lam, modes = _engine.eig_full_dense(torch.from_numpy(A.copy()).cuda(), solver=solver)
+        _check_full(A, lam[0].cpu().numpy(), modes[0].cpu().numpy(), tol=1e-12)
 
 
 def test_eig_full_block_batched():
