@@ -538,11 +538,16 @@ def run_gpu(args):
             filt = "tf32"
             if filt == "tf32":
                 op.slab32(True)                      # single-precision copies of the slab (part of the setup)
-            barrier()
-            t0 = time.perf_counter()
-            theta4, A4, res4, it4 = eig_lowest_dense(op, k4, Z=Z4, filter=filt)
-            barrier()
-            t_solve = time.perf_counter() - t0
+            # two solves: the first one also maps the peer blocks of the TF32 filter (CUDA IPC) and warms NCCL up,
+            # the second one is the steady state a long-running caller sees; both are reported
+            t_solves = []
+            for _ in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                theta4, A4, res4, it4 = eig_lowest_dense(op, k4, Z=Z4, filter=filt)
+                barrier()
+                t_solves.append(time.perf_counter() - t0)
+            t_solve = t_solves[1]
             fl4 = 2.0 * (3 * n4) ** 2 * b4
             extras["c4_dense"] = {
                 "residues": n4, "modes": k4, "ranks": world, "exchange": op.exchange if world > 1 else "none",
@@ -554,7 +559,7 @@ def run_gpu(args):
                 "filter": "residual form, 3-term TF32 split product on the 5th-generation tensor cores (tcgen05.mma "
                           "kind::tf32, TMA operands, TMEM accumulator)" + ("" if world == 1 else
                           "; every rank filters its row slab and stores the rows into the peer-mapped blocks of all ranks"),
-                "solve_seconds": t_solve, "outer_iterations": int(it4),
+                "solve_seconds": t_solve, "first_solve_seconds": t_solves[0], "outer_iterations": int(it4),
                 "max_residual_over_lambda_k": float((res4[:k4].max() / theta4[k4 - 1]).item())}
             if world == 1:
                 hi32, lo32 = op.slab32(True)
