@@ -251,11 +251,15 @@ __device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
 // All CTAs of a group.  Push model: thread t of CTA `me` writes the epoch into the inbox of CTA t and then polls
 // slot t of its OWN inbox, so every CTA spins on lines nobody else reads (one shared flag line polled by 148 SMs
 // saturates its L2 slice and slows every other access of the step).
-__device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, unsigned epoch, unsigned* abort_flag) {
+__device__ __forceinline__ void group_arrive(unsigned* inbox, int me, int G, unsigned epoch) {
     __syncthreads();
     if ((int)threadIdx.x < G) {
         __threadfence();   // the CTA's writes (ordered before this thread by the barrier) become visible first
         st_volatile_u32(inbox + (size_t)threadIdx.x * kInboxPad + me, epoch);
+    }
+}
+__device__ __forceinline__ void group_wait(unsigned* inbox, int me, int G, unsigned epoch, unsigned* abort_flag) {
+    if ((int)threadIdx.x < G) {
         const unsigned* mine = inbox + (size_t)me * kInboxPad + threadIdx.x;
         // acquire: the data loads after the CTA barrier below see the writes.  A member that never arrives (it can
         // only be a fault elsewhere) must not hang the device: after ~10 s of spinning the wait is abandoned, every
@@ -269,6 +273,10 @@ __device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, un
         }
     }
     __syncthreads();
+}
+__device__ __forceinline__ void group_barrier(unsigned* inbox, int me, int G, unsigned epoch, unsigned* abort_flag) {
+    group_arrive(inbox, me, G, epoch);
+    group_wait(inbox, me, G, epoch, abort_flag);
 }
 
 // (Measured dead end: letting the exchanged values carry their own arrival flag -- every slot armed with a NaN
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
     extern __shared__ __align__(16) double tsm[];
     __shared__ double redA[32], redB[32], bc[4];
     __shared__ double partial[kTrdMaxSeg][kTrdMaxRows];
+    __shared__ double pcol[kTrdMaxRows];   // column j+1 of the CTA's rows (for p = tau scal (A a - beta A[:, j+1]))
     const int N = P.N, LD = P.LD, G = P.G;
     const int grp = blockIdx.x / G, c = blockIdx.x % G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -416,30 +425,15 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                 }
                 const double sigma = block_sum_nt1<kTrdThreads>(sig, redB);
                 dj = bc[1];
-                double tau_cur = 0.0, beta = 0.0;
-                if (j < N - 1) {
-                    const double x0 = bc[2];
-                    beta = x0;
-                    if (sigma > 0.0) {
-                        const double nrm = sqrt(fma(x0, x0, sigma));
-                        beta = -copysign(nrm, x0);
-                        tau_cur = (beta - x0) / beta;
-                        const double scal = 1.0 / (x0 - beta);
-                        for (int i = j + tid; i < N; i += kTrdThreads)
-                            if (i >= j + 2) vcur[i] *= scal;
-                    }
-                    if (tid == 1) vcur[j + 1] = 1.0;   // thread 1 owns component j+1
+                // The pass below runs on the RAW column a (vcur): v = scal (a - beta e_{j+1}) gives
+                //   A v = scal (A a - beta A[:, j+1]),
+                // so beta, tau and the scaling (a square root and two divisions) leave the critical path, and v is
+                // normalised in the shadow of the group barrier.
+                const double x0 = bc[2];
+                if (j == N - 1) {
+                    if (owner == c && tid == 0) dd[j] = dj;
+                    break;
                 }
-                __syncthreads();
-                if (owner == c) {
-                    if (tid == 0) {
-                        dd[j] = dj;
-                        if (j < N - 1) { ee[j] = beta; tau[j] = tau_cur; }
-                    }
-                    if (j < N - 1)
-                        for (int i = j + 1 + tid; i < N; i += kTrdThreads) Vt[(size_t)j * LD + i] = vcur[i];
-                }
-                if (j == N - 1) break;
                 TRD_LAP(t_ph1);
                 // ---- pass j: rows i > j of this CTA: apply update j-1, multiply with reflector j.
                 //      Task = (pair of rows, column segment); a lane handles two adjacent columns of both rows.
@@ -503,8 +497,11 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                                 *reinterpret_cast<double2*>(row0 + cc) = x;
                                 acc0 = fma(x.x, vc.x, acc0);
                                 acc0 = fma(x.y, vc.y, acc0);
-                                if (cc == cb && sg == 0)                                   // column j+1
-                                    for (int k = 0; k < ncopies; ++k) __stcg(cout + k * xcopy + i0, (cb == j) ? x.y : x.x);
+                                if (cc == cb && sg == 0) {                                 // column j+1
+                                    const double cv = (cb == j) ? x.y : x.x;
+                                    pcol[2 * pr] = cv;
+                                    for (int k = 0; k < ncopies; ++k) __stcg(cout + k * xcopy + i0, cv);
+                                }
                                 if (two) {
                                     double2 y = a1[u];
                                     y.x -= (v1 * wp.x + w1 * vp.x);
@@ -512,8 +509,11 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                                     *reinterpret_cast<double2*>(row1 + cc) = y;
                                     acc1 = fma(y.x, vc.x, acc1);
                                     acc1 = fma(y.y, vc.y, acc1);
-                                    if (cc == cb && sg == 0)
-                                        for (int k = 0; k < ncopies; ++k) __stcg(cout + k * xcopy + i1, (cb == j) ? y.y : y.x);
+                                    if (cc == cb && sg == 0) {
+                                        const double cv = (cb == j) ? y.y : y.x;
+                                        pcol[2 * pr + 1] = cv;
+                                        for (int k = 0; k < ncopies; ++k) __stcg(cout + k * xcopy + i1, cv);
+                                    }
                                 }
                             }
                         }
@@ -525,16 +525,36 @@ __global__ void __launch_bounds__(kTrdThreads, 1) sytrd_kernel(TrdParams P) {
                         if (two) partial[sg][2 * pr + 1] = acc1;
                     }
                 }
+                double tau_cur = 0.0, beta = x0, scal = 0.0;
+                if (sigma > 0.0) {
+                    const double nrm = sqrt(fma(x0, x0, sigma));
+                    beta = -copysign(nrm, x0);
+                    tau_cur = (beta - x0) / beta;
+                    scal = 1.0 / (x0 - beta);
+                }
                 __syncthreads();
                 if (tid < na) {
                     double acc = 0.0;
                     for (int sg = 0; sg < nseg; ++sg) acc += partial[sg][tid];
                     const int i = c + G * (rmin + tid);
-                    for (int k = 0; k < ncopies; ++k) __stcg(pout + k * xcopy + i, tau_cur * acc);
+                    const double pv = tau_cur * scal * (acc - beta * pcol[tid]);
+                    for (int k = 0; k < ncopies; ++k) __stcg(pout + k * xcopy + i, pv);
                 }
                 TRD_LAP(t_pass);
                 ++epoch;
-                group_barrier(flags, c, G, epoch, P.abort_flag);
+                group_arrive(flags, c, G, epoch);
+                // in the shadow of the barrier: v_j = scal (a - beta e_{j+1}) (v_j[j+1] = 1), the reflector's row of V^T
+                {
+                    const bool mine = (owner == c);
+                    double* vrow = Vt + (size_t)j * LD;
+                    for (int i = j + 1 + tid; i < N; i += kTrdThreads) {
+                        const double v = (i == j + 1) ? 1.0 : vcur[i] * scal;
+                        vcur[i] = v;
+                        if (mine) vrow[i] = v;
+                    }
+                    if (mine && tid == 0) { dd[j] = dj; ee[j] = beta; tau[j] = tau_cur; }
+                }
+                group_wait(flags, c, G, epoch, P.abort_flag);
                 TRD_LAP(t_bar);
                 double* tmp = vprev; vprev = vcur; vcur = tmp;
                 tau_prev = tau_cur;
