@@ -1237,9 +1237,10 @@ int eig_full_tridiag(int B, int N, double* A, double* eigval, double* modes, voi
     if (!ar.ok()) return SCB_ERR_WORKSPACE;
     const int LD = p.LD, L = p.L;
     const int64_t mstride = (int64_t)N * LD, vstride = LD;
-    // 512 threads per CTA: 1,024 (register spills, barrier skew) and 256 (too few warps for the row pass) were slower
-    constexpr int trd_threads = 512;
-    const void* trd_fn = (const void*)sytrd_kernel<512>;
+    // 384 threads per CTA (168 registers, no spills): 512 is 1-3 % slower (spills at 128 registers), 1,024 (barrier
+    // skew) and 256 (too few warps for the row pass) clearly slower
+    constexpr int trd_threads = 384;
+    const void* trd_fn = (const void*)sytrd_kernel<384>;
     SCB_CUDA(cudaFuncSetAttribute(trd_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     SCB_CUDA(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * N + 64));
     const size_t lsmem = sizeof(double) * 2 * kLeaf * (kLeaf + 1);
